@@ -1,0 +1,71 @@
+"""Host-side mirror of dgraph's `codec` package decode path over libdgx.
+
+codec.Decode (codec/codec.go:444-452) and the ApproxLen / ExactLen helpers.
+Decode is one C-ABI call (dgx_decode); the lengths are metadata sums over the
+pack header, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .pb import List, UidPack
+
+
+def view_of(pack: UidPack) -> _lib.PackView:
+    """dgx_pack_view over the pack's arrays (keeps no references: caller keeps `pack` alive)."""
+    v = _lib.PackView()
+    v.block_size = int(pack.block_size)
+    v.nblocks = pack.nblocks
+    v.base = pack.base.ctypes.data
+    v.num_uids = pack.num_uids.ctypes.data
+    v.delta_off = pack.delta_off.ctypes.data
+    v.deltas = pack.deltas.ctypes.data if pack.deltas.size else None
+    return v
+
+
+def ApproxLen(pack: Optional[UidPack]) -> int:
+    """codec.ApproxLen (codec/codec.go:418-423)."""
+    return 0 if pack is None else pack.nblocks * int(pack.block_size)
+
+
+def ExactLen(pack: Optional[UidPack]) -> int:
+    """codec.ExactLen (codec/codec.go:427-440)."""
+    return 0 if pack is None or pack.nblocks == 0 else int(pack.num_uids.sum(dtype=np.uint64))
+
+
+def Decode(pack: Optional[UidPack], seek: int) -> np.ndarray:
+    """codec.Decode(pack, seek): uids from Seek(seek, SeekStart) onward; nil pack -> empty."""
+    if pack is None or pack.nblocks == 0:
+        return np.zeros(0, dtype=np.uint64)
+    lib = _lib.load()
+    pack = pack.normalized()
+    cap = ExactLen(pack)
+    out = np.empty(max(cap, 1), dtype=np.uint64)
+    n = C.c_size_t(0)
+    v = view_of(pack)
+    _lib.check(lib.dgx_decode(C.byref(v), seek, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+    return out[: n.value]
+
+
+def DecodeIntersectSorted(pack: Optional[UidPack], seek: int, lists: Sequence[List]) -> List:
+    """codec.Decode(pack, seek) then algo.IntersectSorted([decoded] + lists), fused on the device."""
+    lib = _lib.load()
+    arrs = [np.zeros(0, np.uint64) if l.Uids is None else l.Uids for l in lists]
+    k = len(arrs)
+    ptrs = (C.c_void_p * max(k, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (C.c_size_t * max(k, 1))(*[a.size for a in arrs])
+    cap = min([a.size for a in arrs] + [ExactLen(pack)])
+    out = np.empty(max(cap, 1), dtype=np.uint64)
+    n = C.c_size_t(0)
+    if pack is None or pack.nblocks == 0:
+        vp = None
+    else:
+        pack = pack.normalized()
+        v = view_of(pack)
+        vp = C.byref(v)
+    _lib.check(lib.dgx_decode_intersect_sorted(vp, seek, ptrs, lens, k, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+    return List(out[: n.value])

@@ -1,0 +1,858 @@
+// dgx_api.cu -- libdgx.so: C ABI (include/dgx.h) over the sm_100a kernels.
+//
+// Host responsibilities only: lane (stream + workspace) management, building the
+// small task / list descriptor tables the kernels read, host<->device copies for
+// the host-pointer entry points.  No set-operation or decode arithmetic runs on
+// the CPU here: if CUDA is unavailable every entry point fails with
+// DGX_ERR_NODEV / DGX_ERR_CUDA (the cgo shim then stays on the Go path).
+#include "../../include/dgx.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "decode_kernel.cuh"
+#include "filter_kernel.cuh"
+#include "merge_kernel.cuh"
+
+using namespace dgx;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? DGX_ERR_OOM : DGX_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* dgx_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------
+// global state
+// ---------------------------------------------------------------------------
+struct Stats {
+    std::atomic<uint64_t> calls{0}, uids_in{0}, uids_out{0}, h2d{0}, d2h{0}, launches{0};
+};
+static Stats g_stats;
+static std::mutex g_mu;
+static int g_device = -1;
+static std::vector<dgx_lane*> g_pool;  // idle lanes for the host-pointer entry points
+static u32 g_stream_ratio = 16;
+
+// ---------------------------------------------------------------------------
+// arenas
+// ---------------------------------------------------------------------------
+// Device scratch: bump allocator, reset at the start of every public op (safe:
+// later work on the same stream is ordered after earlier kernels).
+struct DevArena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<void*> retired;  // old chunks still referenced by queued work
+    int alloc(size_t bytes, void** out) {
+        bytes = (bytes + 255) & ~size_t(255);
+        if (used + bytes > cap) {
+            size_t ncap = std::max(cap * 2, used + bytes + (size_t(1) << 20));
+            void* nb = nullptr;
+            cudaError_t e = cudaMalloc(&nb, ncap);
+            if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed: %s", ncap, cudaGetErrorString(e));
+            if (base) retired.push_back(base);  // pointers handed out earlier in this op stay valid
+            base = (char*)nb;
+            cap = ncap;
+            used = 0;
+        }
+        *out = base + used;
+        used += bytes;
+        return DGX_OK;
+    }
+    void reset() { used = 0; }
+    void release_retired() {
+        for (void* p : retired) cudaFree(p);
+        retired.clear();
+    }
+    void destroy() {
+        release_retired();
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = used = 0;
+    }
+};
+
+// Pinned host staging for descriptor tables: async H2D copies read from it
+// later, so it is only recycled at lane sync.
+struct HostArena {
+    struct Chunk { char* p; size_t cap, used; };
+    std::vector<Chunk> chunks;
+    int alloc(size_t bytes, void** out) {
+        bytes = (bytes + 63) & ~size_t(63);
+        if (chunks.empty() || chunks.back().used + bytes > chunks.back().cap) {
+            size_t ncap = std::max(bytes, chunks.empty() ? (size_t(1) << 20) : chunks.back().cap * 2);
+            void* p = nullptr;
+            cudaError_t e = cudaMallocHost(&p, ncap);
+            if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMallocHost(%zu) failed: %s", ncap, cudaGetErrorString(e));
+            chunks.push_back({(char*)p, ncap, 0});
+        }
+        Chunk& c = chunks.back();
+        *out = c.p + c.used;
+        c.used += bytes;
+        return DGX_OK;
+    }
+    void reset() {  // keep the largest (last) chunk
+        while (chunks.size() > 1) {
+            cudaFreeHost(chunks.front().p);
+            chunks.erase(chunks.begin());
+        }
+        if (!chunks.empty()) chunks.back().used = 0;
+    }
+    void destroy() {
+        for (auto& c : chunks) cudaFreeHost(c.p);
+        chunks.clear();
+    }
+};
+
+struct dgx_lane {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevArena ws;
+    HostArena host;
+    int* d_err = nullptr;   // device error flag (out_cap overflow)
+    int* h_err = nullptr;   // pinned mirror
+    uint64_t* h_word = nullptr;  // pinned scratch for lengths (8 words)
+    uint64_t launches = 0;
+};
+
+// ---------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------
+extern "C" int dgx_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device >= 0) return DGX_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(DGX_ERR_NODEV, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= n) return fail(DGX_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(DGX_ERR_NODEV, "libdgx is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(sizeof(DWarpSmem) * D_WARPS)));
+    if (const char* s = getenv("DGX_STREAM_RATIO")) {
+        int v = atoi(s);
+        if (v >= 0) g_stream_ratio = (u32)v;
+    }
+    g_device = device;
+    return DGX_OK;
+}
+
+extern "C" void dgx_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (dgx_lane* l : g_pool) dgx_lane_destroy(l);
+    g_pool.clear();
+    g_device = -1;
+}
+
+extern "C" int dgx_describe(char* buf, size_t n) {
+    int rc = dgx_init(-1);
+    if (rc != DGX_OK) return rc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    snprintf(buf, n, "libdgx sm_100a | device %d: %s, %d SMs, %.1f GB | filter tile %d, merge tile %d",
+             g_device, prop.name, prop.multiProcessorCount, prop.totalGlobalMem / 1e9, F_TA, M_T);
+    return DGX_OK;
+}
+
+extern "C" void* dgx_host_alloc(size_t bytes) {
+    if (dgx_init(-1) != DGX_OK) return nullptr;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void dgx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" void dgx_get_stats(dgx_stats* out) {
+    out->calls = g_stats.calls;
+    out->uids_in = g_stats.uids_in;
+    out->uids_out = g_stats.uids_out;
+    out->h2d_bytes = g_stats.h2d;
+    out->d2h_bytes = g_stats.d2h;
+    out->kernel_launches = g_stats.launches;
+}
+
+extern "C" dgx_lane* dgx_lane_create(int device, void* stream) {
+    if (dgx_init(device) != DGX_OK) return nullptr;
+    if (device < 0) device = g_device;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    dgx_lane* l = new dgx_lane();
+    l->device = device;
+    if (stream) {
+        l->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; return nullptr; }
+        l->own_stream = true;
+    }
+    if (cudaMalloc(&l->d_err, 256) != cudaSuccess || cudaMallocHost(&l->h_err, 256) != cudaSuccess) {
+        fail(DGX_ERR_OOM, "lane allocation failed");
+        delete l;
+        return nullptr;
+    }
+    l->h_word = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(l->h_err) + 64);
+    *l->h_err = 0;
+    cudaMemsetAsync(l->d_err, 0, 256, l->stream);
+    return l;
+}
+
+extern "C" void dgx_lane_destroy(dgx_lane* l) {
+    if (!l) return;
+    cudaSetDevice(l->device);
+    cudaStreamSynchronize(l->stream);
+    l->ws.destroy();
+    l->host.destroy();
+    if (l->d_err) cudaFree(l->d_err);
+    if (l->h_err) cudaFreeHost(l->h_err);
+    if (l->own_stream) cudaStreamDestroy(l->stream);
+    delete l;
+}
+
+extern "C" void* dgx_lane_stream(dgx_lane* l) { return (void*)l->stream; }
+extern "C" uint64_t dgx_lane_launches(const dgx_lane* l) { return l->launches; }
+
+extern "C" int dgx_lane_sync(dgx_lane* l) {
+    CK(cudaMemcpyAsync(l->h_err, l->d_err, sizeof(int), cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaStreamSynchronize(l->stream));
+    l->host.reset();
+    l->ws.release_retired();
+    if (*l->h_err) {
+        *l->h_err = 0;
+        CK(cudaMemsetAsync(l->d_err, 0, sizeof(int), l->stream));
+        return fail(DGX_ERR_CAP, "result does not fit out_cap");
+    }
+    return DGX_OK;
+}
+
+extern "C" void* dgx_dev_alloc(size_t bytes) {
+    if (dgx_init(-1) != DGX_OK) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void dgx_dev_free(void* p) {
+    if (p) cudaFree(p);
+}
+extern "C" int dgx_memcpy_h2d(dgx_lane* l, void* d, const void* h, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, l->stream));
+    g_stats.h2d += bytes;
+    return DGX_OK;
+}
+extern "C" int dgx_memcpy_d2h(dgx_lane* l, void* h, const void* d, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, l->stream));
+    g_stats.d2h += bytes;
+    return DGX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// filter (intersect / k-way intersect / difference), device level
+// ---------------------------------------------------------------------------
+struct ListDesc {
+    const uint64_t* ptr;
+    size_t len;
+    const uint64_t* dyn_len;
+};
+
+// Queries q own lists [k_off[q], k_off[q+1]).  Results -> d_out / d_out_off.
+static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const size_t* k_off, size_t nq,
+                             uint64_t* d_out, size_t out_cap, uint64_t* d_out_off) {
+    if (nq == 0) {
+        CK(cudaMemsetAsync(d_out_off, 0, sizeof(uint64_t), l->stream));
+        return DGX_OK;
+    }
+    const size_t nlists = k_off[nq] - k_off[0];
+    void *h_raw, *d_raw;
+    const size_t tasks_b = nq * sizeof(FTask), lists_b = (nlists + 1) * sizeof(FList);
+    int rc = l->host.alloc(tasks_b + lists_b, &h_raw);
+    if (rc) return rc;
+    FTask* ht = (FTask*)h_raw;
+    FList* hl = (FList*)((char*)h_raw + tasks_b);
+    uint64_t ntiles = 0, uids_in = 0;
+    size_t li = 0;
+    std::vector<size_t> order;
+    for (size_t q = 0; q < nq; ++q) {
+        const size_t k0 = k_off[q], k1 = k_off[q + 1];
+        const size_t k = k1 - k0;
+        if (k == 0) return fail(DGX_ERR_ARG, "query %zu has no lists", q);
+        if (op == DGX_OP_DIFFERENCE && k != 2) return fail(DGX_ERR_ARG, "difference takes exactly two lists");
+        order.resize(k);
+        std::iota(order.begin(), order.end(), k0);
+        if (op == DGX_OP_INTERSECT)  // drive from the shortest list (algo/uidlist.go:309-311)
+            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return lists[x].len < lists[y].len; });
+        ht[q].tile_base = ntiles;
+        ht[q].list_first = (u32)li;
+        ht[q].k = (u32)k;
+        for (size_t i = 0; i < k; ++i) {
+            const ListDesc& L = lists[order[i]];
+            hl[li].ptr = (const u64*)L.ptr;
+            hl[li].len = L.len;
+            hl[li].dyn_len = (const u64*)L.dyn_len;
+            uids_in += L.len;
+            ++li;
+        }
+        const uint64_t lenA = lists[order[0]].len;
+        ntiles += std::max<uint64_t>(1, (lenA + F_TA - 1) / F_TA);
+    }
+    if (ntiles > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large (%llu tiles)", (unsigned long long)ntiles);
+    const size_t status_b = ntiles * sizeof(u64) + 64;
+    rc = l->ws.alloc(tasks_b + lists_b + status_b, &d_raw);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_raw, h_raw, tasks_b + lists_b, cudaMemcpyHostToDevice, l->stream));
+    char* d_status = (char*)d_raw + tasks_b + lists_b;
+    CK(cudaMemsetAsync(d_status, 0, status_b, l->stream));
+    FParams P;
+    P.tasks = (const FTask*)d_raw;
+    P.lists = (const FList*)((char*)d_raw + tasks_b);
+    P.ntasks = (u32)nq;
+    P.ntiles = (u32)ntiles;
+    P.op = op;
+    P.stream_ratio = g_stream_ratio;
+    P.out = (u64*)d_out;
+    P.out_cap = out_cap;
+    P.out_off = (u64*)d_out_off;
+    P.status = (u64*)d_status;
+    P.ticket = (u32*)(d_status + ntiles * sizeof(u64));
+    P.err = l->d_err;
+    filter_kernel<<<(unsigned)ntiles, F_NT, 0, l->stream>>>(P);
+    CK(cudaGetLastError());
+    l->launches += 1;
+    g_stats.launches += 1;
+    g_stats.uids_in += uids_in;
+    return DGX_OK;
+}
+
+extern "C" int dgx_dev_filter_batch(dgx_lane* l, int op, const uint64_t* const* d_lists, const size_t* lens,
+                                    const size_t* k_off, size_t nq, uint64_t* d_out, size_t out_cap,
+                                    uint64_t* d_out_off) {
+    if (!l || (op != DGX_OP_INTERSECT && op != DGX_OP_DIFFERENCE)) return fail(DGX_ERR_ARG, "bad lane/op");
+    CK(cudaSetDevice(l->device));
+    l->ws.reset();
+    const size_t nlists = nq ? k_off[nq] : 0;
+    std::vector<ListDesc> ld(nlists);
+    for (size_t i = 0; i < nlists; ++i) ld[i] = {d_lists[i], lens[i], nullptr};
+    g_stats.calls += 1;
+    return filter_batch_impl(l, op, ld.data(), k_off, nq, d_out, out_cap, d_out_off);
+}
+
+// ---------------------------------------------------------------------------
+// MergeSorted, device level: tree of batched 2-way unions
+// ---------------------------------------------------------------------------
+static int merge_sorted_impl(dgx_lane* l, const ListDesc* lists, size_t k, uint64_t* d_out, size_t out_cap,
+                             uint64_t* d_out_len) {
+    // nil / empty lists are skipped (algo/uidlist.go:400-403)
+    std::vector<MRef> cur;
+    std::vector<uint64_t> ub;
+    uint64_t total = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (lists[i].ptr == nullptr || lists[i].len == 0) continue;
+        cur.push_back(MRef{(const u64*)lists[i].ptr, nullptr, (u64)lists[i].len});
+        ub.push_back(lists[i].len);
+        total += lists[i].len;
+    }
+    g_stats.uids_in += total;
+    if (cur.empty()) {
+        CK(cudaMemsetAsync(d_out_len, 0, sizeof(uint64_t), l->stream));
+        return DGX_OK;
+    }
+    if (out_cap < total) return fail(DGX_ERR_CAP, "MergeSorted needs out_cap >= sum(lens) = %llu", (unsigned long long)total);
+    // number of levels; a single list still takes one pass (in-list de-duplication)
+    int levels = 0;
+    for (size_t n = cur.size(); n > 1; n = (n + 1) / 2) ++levels;
+    if (levels == 0) levels = 1;
+    void* d_tmp = nullptr;
+    int rc;
+    if (levels > 1) {
+        rc = l->ws.alloc(total * sizeof(u64), &d_tmp);
+        if (rc) return rc;
+    }
+    // plan all levels on the host
+    struct Level { std::vector<MTask> tasks; uint64_t ntiles; u64* out; size_t off_index; };
+    std::vector<Level> plan(levels);
+    size_t off_words = 0, task_count = 0;
+    uint64_t tiles_total = 0;
+    for (int lv = 0; lv < levels; ++lv) {
+        Level& L = plan[lv];
+        L.out = ((levels - 1 - lv) % 2 == 0) ? (u64*)d_out : (u64*)d_tmp;
+        const size_t n = cur.size();
+        const size_t nt = (n + 1) / 2;
+        L.tasks.resize(nt);
+        L.ntiles = 0;
+        L.off_index = off_words;
+        std::vector<uint64_t> nub(nt);
+        for (size_t t = 0; t < nt; ++t) {
+            MTask& T = L.tasks[t];
+            T.tile_base = L.ntiles;
+            T.a = cur[2 * t];
+            uint64_t u = ub[2 * t];
+            if (2 * t + 1 < n) { T.b = cur[2 * t + 1]; u += ub[2 * t + 1]; }
+            else T.b = MRef{nullptr, nullptr, 0};
+            nub[t] = u;
+            L.ntiles += std::max<uint64_t>(1, (u + M_T - 1) / M_T);
+        }
+        if (L.ntiles > 0x7fffffffull) return fail(DGX_ERR_ARG, "merge too large");
+        off_words += nt + 1;
+        task_count += nt;
+        tiles_total += L.ntiles;
+        // next level's inputs are slices of this level's compact output (offsets patched below)
+        cur.assign(nt, MRef{L.out, nullptr, 0});
+        ub = nub;
+        for (size_t t = 0; t < nt; ++t) { cur[t].len = nub[t]; cur[t].off = (const u64*)(uintptr_t)(L.off_index + t + 1); }
+    }
+    // device layout: [off words][tasks][status + tickets]
+    const size_t off_b = off_words * sizeof(u64);
+    const size_t tasks_b = task_count * sizeof(MTask);
+    const size_t status_b = (tiles_total + 2 * levels) * sizeof(u64);
+    void *d_raw, *h_raw;
+    rc = l->ws.alloc(off_b + tasks_b + status_b, &d_raw);
+    if (rc) return rc;
+    rc = l->host.alloc(tasks_b, &h_raw);
+    if (rc) return rc;
+    u64* d_off = (u64*)d_raw;
+    MTask* d_tasks = (MTask*)((char*)d_raw + off_b);
+    u64* d_status = (u64*)((char*)d_raw + off_b + tasks_b);
+    // patch symbolic offsets (index+1 encoded in the pointer) into device addresses
+    MTask* ht = (MTask*)h_raw;
+    size_t ti = 0;
+    for (int lv = 0; lv < levels; ++lv)
+        for (MTask T : plan[lv].tasks) {
+            if (lv > 0) {
+                T.a.off = d_off + ((uintptr_t)T.a.off - 1);
+                if (T.b.base) T.b.off = d_off + ((uintptr_t)T.b.off - 1);
+            }
+            ht[ti++] = T;
+        }
+    CK(cudaMemcpyAsync(d_tasks, ht, tasks_b, cudaMemcpyHostToDevice, l->stream));
+    CK(cudaMemsetAsync(d_status, 0, status_b, l->stream));
+    size_t tpos = 0;
+    uint64_t spos = 0;
+    for (int lv = 0; lv < levels; ++lv) {
+        Level& L = plan[lv];
+        MParams P;
+        P.tasks = d_tasks + tpos;
+        P.ntasks = (u32)L.tasks.size();
+        P.ntiles = (u32)L.ntiles;
+        P.out = L.out;
+        P.out_cap = (L.out == (u64*)d_out) ? out_cap : total;
+        P.out_off = d_off + L.off_index;
+        P.status = d_status + spos;
+        P.ticket = (u32*)(d_status + spos + L.ntiles);
+        P.err = l->d_err;
+        merge_kernel<<<(unsigned)L.ntiles, M_NT, 0, l->stream>>>(P);
+        CK(cudaGetLastError());
+        l->launches += 1;
+        g_stats.launches += 1;
+        tpos += L.tasks.size();
+        spos += L.ntiles + 2;
+    }
+    CK(cudaMemcpyAsync(d_out_len, d_off + plan[levels - 1].off_index + 1, sizeof(u64), cudaMemcpyDeviceToDevice, l->stream));
+    return DGX_OK;
+}
+
+extern "C" int dgx_dev_merge_sorted(dgx_lane* l, const uint64_t* const* d_lists, const size_t* lens, size_t k,
+                                    uint64_t* d_out, size_t out_cap, uint64_t* d_out_len) {
+    if (!l) return fail(DGX_ERR_ARG, "null lane");
+    CK(cudaSetDevice(l->device));
+    l->ws.reset();
+    std::vector<ListDesc> ld(k);
+    for (size_t i = 0; i < k; ++i) ld[i] = {d_lists[i], lens[i], nullptr};
+    g_stats.calls += 1;
+    return merge_sorted_impl(l, ld.data(), k, d_out, out_cap, d_out_len);
+}
+
+// ---------------------------------------------------------------------------
+// UidPack decode, device level
+// ---------------------------------------------------------------------------
+struct dgx_dev_pack {
+    DPack pk;
+    void* d_mem = nullptr;
+    size_t bytes = 0;
+    size_t exact_len = 0;
+    uint32_t block_size = 0;
+};
+
+// Lays the pack out in one device allocation:
+// [base u64 | delta_off u64 (n+1) | uid_off u64 (n+1) | num u32 | deltas (16-aligned, +48 slack)]
+static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_null, DevArena* arena,
+                            dgx_dev_pack* out) {
+    const size_t nb = v ? v->nblocks : 0;
+    const size_t dbytes = nb ? (size_t)v->delta_off[nb] : 0;
+    const size_t o_base = 0;
+    const size_t o_doff = o_base + nb * 8;
+    const size_t o_uoff = o_doff + (nb + 1) * 8;
+    const size_t o_num = o_uoff + (nb + 1) * 8;
+    const size_t o_del = (o_num + nb * 4 + 15) & ~size_t(15);
+    const size_t total = o_del + ((dbytes + 15) & ~size_t(15)) + 48;
+    void* d_mem = d_mem_or_null;
+    int rc;
+    if (!d_mem) {
+        if (arena) { rc = arena->alloc(total, &d_mem); if (rc) return rc; }
+        else { cudaError_t e = cudaMalloc(&d_mem, total); if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e)); }
+    }
+    // uid_off (exclusive prefix of NumUids) and max NumUids: layout metadata, computed while flattening
+    void* h_raw;
+    rc = l->host.alloc((nb + 1) * 8, &h_raw);
+    if (rc) return rc;
+    uint64_t* h_uoff = (uint64_t*)h_raw;
+    uint64_t acc = 0;
+    uint32_t max_num = 0;
+    for (size_t i = 0; i < nb; ++i) {
+        h_uoff[i] = acc;
+        acc += v->num_uids[i];
+        max_num = std::max(max_num, v->num_uids[i]);
+    }
+    h_uoff[nb] = acc;
+    char* d = (char*)d_mem;
+    if (nb) {
+        CK(cudaMemcpyAsync(d + o_base, v->base, nb * 8, cudaMemcpyHostToDevice, l->stream));
+        CK(cudaMemcpyAsync(d + o_doff, v->delta_off, (nb + 1) * 8, cudaMemcpyHostToDevice, l->stream));
+        CK(cudaMemcpyAsync(d + o_num, v->num_uids, nb * 4, cudaMemcpyHostToDevice, l->stream));
+        if (dbytes) CK(cudaMemcpyAsync(d + o_del, v->deltas, dbytes, cudaMemcpyHostToDevice, l->stream));
+    }
+    CK(cudaMemcpyAsync(d + o_uoff, h_uoff, (nb + 1) * 8, cudaMemcpyHostToDevice, l->stream));
+    CK(cudaMemsetAsync(d + o_del + dbytes, 0, total - o_del - dbytes, l->stream));
+    g_stats.h2d += nb * 8 + (nb + 1) * 16 + nb * 4 + dbytes;
+    out->pk.nblocks = nb;
+    out->pk.base = (const u64*)(d + o_base);
+    out->pk.delta_off = (const u64*)(d + o_doff);
+    out->pk.uid_off = (const u64*)(d + o_uoff);
+    out->pk.num = (const u32*)(d + o_num);
+    out->pk.deltas = (const unsigned char*)(d + o_del);
+    out->pk.max_num = max_num;
+    out->d_mem = d_mem;
+    out->bytes = total;
+    out->exact_len = acc;
+    out->block_size = v ? v->block_size : 0;
+    return DGX_OK;
+}
+
+extern "C" int dgx_dev_pack_upload(dgx_lane* l, const dgx_pack_view* v, dgx_dev_pack** out) {
+    if (!l || !out) return fail(DGX_ERR_ARG, "null argument");
+    CK(cudaSetDevice(l->device));
+    dgx_dev_pack* pk = new dgx_dev_pack();
+    int rc = pack_upload_impl(l, v, nullptr, nullptr, pk);
+    if (rc) { delete pk; return rc; }
+    // the pinned uid_off staging must outlive the async copy
+    CK(cudaStreamSynchronize(l->stream));
+    *out = pk;
+    return DGX_OK;
+}
+extern "C" void dgx_dev_pack_free(dgx_dev_pack* pk) {
+    if (!pk) return;
+    if (pk->d_mem) cudaFree(pk->d_mem);
+    delete pk;
+}
+extern "C" size_t dgx_dev_pack_exact_len(const dgx_dev_pack* pk) { return pk ? pk->exact_len : 0; }
+extern "C" size_t dgx_dev_pack_bytes(const dgx_dev_pack* pk) { return pk ? pk->bytes : 0; }
+
+static int decode_impl(dgx_lane* l, const DPack& pk, uint64_t seek, uint64_t* d_out, size_t out_cap,
+                       uint64_t* d_out_len) {
+    void* d_seek;
+    int rc = l->ws.alloc(sizeof(DSeek), &d_seek);
+    if (rc) return rc;
+    decode_seek_kernel<<<1, 32, 0, l->stream>>>(pk, seek, (DSeek*)d_seek, (u64*)d_out_len, out_cap, l->d_err);
+    CK(cudaGetLastError());
+    l->launches += 1;
+    g_stats.launches += 1;
+    if (pk.nblocks) {
+        const uint64_t warps = (pk.nblocks + D_BPW - 1) / D_BPW;
+        const uint64_t ctas = (warps + D_WARPS - 1) / D_WARPS;
+        decode_kernel<<<(unsigned)ctas, D_NT, sizeof(DWarpSmem) * D_WARPS, l->stream>>>(pk, (const DSeek*)d_seek, (u64*)d_out, out_cap);
+        CK(cudaGetLastError());
+        l->launches += 1;
+        g_stats.launches += 1;
+    }
+    return DGX_OK;
+}
+
+extern "C" int dgx_dev_decode(dgx_lane* l, const dgx_dev_pack* pk, uint64_t seek, uint64_t* d_out, size_t out_cap,
+                              uint64_t* d_out_len) {
+    if (!l || !pk) return fail(DGX_ERR_ARG, "null argument");
+    CK(cudaSetDevice(l->device));
+    l->ws.reset();
+    g_stats.calls += 1;
+    g_stats.uids_in += pk->exact_len;
+    return decode_impl(l, pk->pk, seek, d_out, out_cap, d_out_len);
+}
+
+// ---------------------------------------------------------------------------
+// host-pointer entry points
+// ---------------------------------------------------------------------------
+struct LaneLease {
+    dgx_lane* l = nullptr;
+    int rc = DGX_OK;
+    LaneLease() {
+        rc = dgx_init(-1);
+        if (rc) return;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            if (!g_pool.empty()) { l = g_pool.back(); g_pool.pop_back(); }
+        }
+        if (!l) {
+            l = dgx_lane_create(g_device, nullptr);
+            if (!l) rc = fail(DGX_ERR_CUDA, "cannot create lane: %s", g_err.c_str());
+        }
+        if (l) { cudaSetDevice(l->device); l->ws.reset(); }
+    }
+    ~LaneLease() {
+        if (!l) return;
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_pool.push_back(l);
+    }
+};
+
+static int upload_list(dgx_lane* l, const uint64_t* h, size_t n, uint64_t** d) {
+    void* p;
+    int rc = l->ws.alloc((n + 2) * sizeof(uint64_t), &p);
+    if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(p, h, n * sizeof(uint64_t), cudaMemcpyHostToDevice, l->stream));
+    g_stats.h2d += n * sizeof(uint64_t);
+    *d = (uint64_t*)p;
+    return DGX_OK;
+}
+
+// sync, read the result length at d_len, copy `len` values to the host
+static int finish_to_host(dgx_lane* l, const uint64_t* d_len, const uint64_t* d_out, uint64_t* out, size_t out_cap,
+                          size_t* out_len) {
+    CK(cudaMemcpyAsync(l->h_word, d_len, sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    int rc = dgx_lane_sync(l);
+    if (rc) return rc;
+    const uint64_t n = l->h_word[0];
+    if (n > out_cap) return fail(DGX_ERR_CAP, "result (%llu) does not fit out_cap (%zu)", (unsigned long long)n, out_cap);
+    if (n) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+        CK(cudaStreamSynchronize(l->stream));
+    }
+    g_stats.d2h += n * sizeof(uint64_t) + 8;
+    g_stats.uids_out += n;
+    if (out_len) *out_len = (size_t)n;
+    return DGX_OK;
+}
+
+static int filter_host(int op, const uint64_t* const* lists, const size_t* lens, size_t k, uint64_t* out,
+                       size_t out_cap, size_t* out_len) {
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    std::vector<ListDesc> ld(k);
+    size_t cap = SIZE_MAX;
+    for (size_t i = 0; i < k; ++i) {
+        uint64_t* d;
+        int rc = upload_list(l, lists[i], lens[i], &d);
+        if (rc) return rc;
+        ld[i] = {d, lens[i], nullptr};
+        if (op == DGX_OP_INTERSECT) cap = std::min(cap, lens[i]);
+    }
+    if (op == DGX_OP_DIFFERENCE) cap = lens[0];
+    void *d_out, *d_off;
+    int rc = l->ws.alloc((cap + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc(2 * sizeof(uint64_t), &d_off);
+    if (rc) return rc;
+    const size_t k_off[2] = {0, k};
+    rc = filter_batch_impl(l, op, ld.data(), k_off, 1, (uint64_t*)d_out, cap, (uint64_t*)d_off);
+    if (rc) return rc;
+    return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, out, out_cap, out_len);
+}
+
+extern "C" int dgx_intersect2(const uint64_t* u, size_t n, const uint64_t* v, size_t m, uint64_t* out,
+                              size_t out_cap, size_t* out_len) {
+    const uint64_t* lists[2] = {u, v};
+    const size_t lens[2] = {n, m};
+    return filter_host(DGX_OP_INTERSECT, lists, lens, 2, out, out_cap, out_len);
+}
+
+extern "C" int dgx_intersect_sorted(const uint64_t* const* lists, const size_t* lens, size_t k, uint64_t* out,
+                                    size_t out_cap, size_t* out_len) {
+    if (k == 0) {  // IntersectSorted of no lists is the empty list (algo/uidlist.go:298-300)
+        if (out_len) *out_len = 0;
+        return DGX_OK;
+    }
+    return filter_host(DGX_OP_INTERSECT, lists, lens, k, out, out_cap, out_len);
+}
+
+extern "C" int dgx_difference(const uint64_t* u, size_t n, const uint64_t* v, size_t m, uint64_t* out,
+                              size_t out_cap, size_t* out_len) {
+    const uint64_t* lists[2] = {u, v};
+    const size_t lens[2] = {n, m};
+    return filter_host(DGX_OP_DIFFERENCE, lists, lens, 2, out, out_cap, out_len);
+}
+
+extern "C" int dgx_merge_sorted(const uint64_t* const* lists, const size_t* lens, size_t k, uint64_t* out,
+                                size_t out_cap, size_t* out_len) {
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    std::vector<ListDesc> ld(k);
+    size_t total = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (lists[i] == nullptr || lens[i] == 0) { ld[i] = {nullptr, 0, nullptr}; continue; }
+        uint64_t* d;
+        int rc = upload_list(l, lists[i], lens[i], &d);
+        if (rc) return rc;
+        ld[i] = {d, lens[i], nullptr};
+        total += lens[i];
+    }
+    void *d_out, *d_len;
+    int rc = l->ws.alloc((total + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc(64, &d_len);
+    if (rc) return rc;
+    rc = merge_sorted_impl(l, ld.data(), k, (uint64_t*)d_out, total, (uint64_t*)d_len);
+    if (rc) return rc;
+    return finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, out, out_cap, out_len);
+}
+
+extern "C" int dgx_intersect_batch(const uint64_t* a, const uint64_t* a_off, const uint64_t* b,
+                                   const uint64_t* b_off, size_t npairs, uint64_t* out, uint64_t* out_off,
+                                   size_t out_cap) {
+    if (npairs == 0) { if (out_off) out_off[0] = 0; return DGX_OK; }
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    const size_t na = a_off[npairs] - a_off[0], nbv = b_off[npairs] - b_off[0];
+    uint64_t *d_a, *d_b;
+    int rc = upload_list(l, a + a_off[0], na, &d_a);
+    if (rc) return rc;
+    rc = upload_list(l, b + b_off[0], nbv, &d_b);
+    if (rc) return rc;
+    std::vector<ListDesc> ld(2 * npairs);
+    std::vector<size_t> k_off(npairs + 1);
+    size_t cap = 0;
+    for (size_t i = 0; i < npairs; ++i) {
+        const size_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
+        ld[2 * i] = {d_a + (a_off[i] - a_off[0]), la, nullptr};
+        ld[2 * i + 1] = {d_b + (b_off[i] - b_off[0]), lb, nullptr};
+        k_off[i] = 2 * i;
+        cap += std::min(la, lb);
+    }
+    k_off[npairs] = 2 * npairs;
+    void *d_out, *d_off;
+    rc = l->ws.alloc((cap + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc((npairs + 1) * sizeof(uint64_t), &d_off);
+    if (rc) return rc;
+    rc = filter_batch_impl(l, DGX_OP_INTERSECT, ld.data(), k_off.data(), npairs, (uint64_t*)d_out, cap, (uint64_t*)d_off);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_off, d_off, (npairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    rc = dgx_lane_sync(l);
+    if (rc) return rc;
+    const uint64_t n = out_off[npairs];
+    if (n > out_cap) return fail(DGX_ERR_CAP, "batch result (%llu) does not fit out_cap (%zu)", (unsigned long long)n, out_cap);
+    if (n) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+        CK(cudaStreamSynchronize(l->stream));
+    }
+    g_stats.d2h += (n + npairs + 1) * sizeof(uint64_t);
+    g_stats.uids_out += n;
+    return DGX_OK;
+}
+
+extern "C" int dgx_decode(const dgx_pack_view* p, uint64_t seek, uint64_t* out, size_t out_cap, size_t* out_len) {
+    if (!p || p->nblocks == 0) {  // nil / empty pack decodes to the empty list (codec/codec.go:445-446)
+        if (out_len) *out_len = 0;
+        return DGX_OK;
+    }
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    dgx_dev_pack pk;
+    int rc = pack_upload_impl(l, p, nullptr, &l->ws, &pk);
+    if (rc) return rc;
+    g_stats.uids_in += pk.exact_len;
+    void *d_out, *d_len;
+    rc = l->ws.alloc((pk.exact_len + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc(64, &d_len);
+    if (rc) return rc;
+    rc = decode_impl(l, pk.pk, seek, (uint64_t*)d_out, pk.exact_len, (uint64_t*)d_len);
+    if (rc) return rc;
+    return finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, out, out_cap, out_len);
+}
+
+extern "C" int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek, const uint64_t* const* lists,
+                                           const size_t* lens, size_t k, uint64_t* out, size_t out_cap,
+                                           size_t* out_len) {
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    std::vector<ListDesc> ld(k + 1);
+    int rc;
+    size_t cap = SIZE_MAX;
+    for (size_t i = 0; i < k; ++i) {
+        uint64_t* d;
+        rc = upload_list(l, lists[i], lens[i], &d);
+        if (rc) return rc;
+        ld[i + 1] = {d, lens[i], nullptr};
+        cap = std::min(cap, lens[i]);
+    }
+    void *d_dec = nullptr, *d_len;
+    rc = l->ws.alloc(64, &d_len);
+    if (rc) return rc;
+    size_t exact = 0;
+    if (p && p->nblocks) {
+        dgx_dev_pack pk;
+        rc = pack_upload_impl(l, p, nullptr, &l->ws, &pk);
+        if (rc) return rc;
+        exact = pk.exact_len;
+        rc = l->ws.alloc((exact + 2) * sizeof(uint64_t), &d_dec);
+        if (rc) return rc;
+        rc = decode_impl(l, pk.pk, seek, (uint64_t*)d_dec, exact, (uint64_t*)d_len);
+        if (rc) return rc;
+    } else {
+        rc = l->ws.alloc(16, &d_dec);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(d_len, 0, 8, l->stream));
+    }
+    g_stats.uids_in += exact;
+    ld[0] = {(const uint64_t*)d_dec, exact, (const uint64_t*)d_len};
+    cap = std::min(cap, exact);
+    void *d_out, *d_off;
+    rc = l->ws.alloc((cap + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc(2 * sizeof(uint64_t), &d_off);
+    if (rc) return rc;
+    const size_t k_off[2] = {0, k + 1};
+    rc = filter_batch_impl(l, DGX_OP_INTERSECT, ld.data(), k_off, 1, (uint64_t*)d_out, cap, (uint64_t*)d_off);
+    if (rc) return rc;
+    return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, out, out_cap, out_len);
+}

@@ -1,0 +1,185 @@
+/*
+ * dgx.h -- C ABI of libdgx.so: B200-native (sm_100a) sorted-uint64 posting-list
+ * set operations and UidPack decode, the drop-in for dgraph's algo/ + codec/
+ * hot path.
+ *
+ * The reference has no plugin interface for this path: callers invoke
+ * package-level Go functions.  The boundary is therefore the Go signatures
+ * themselves; a cgo shim (go/algo_dgx.go) keeps each
+ * signature and forwards to the entry point listed beside it here.  All
+ * citations are relative to /root/reference.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Inputs are BORROWED for the duration of
+ *    the call (Go memory may move afterwards): every entry point has finished
+ *    reading its inputs when it returns.  Outputs are CALLER-ALLOCATED; the
+ *    library writes at most out_cap values and reports the length.
+ *  - Return value: DGX_OK (0) or a negative dgx_status.  The reference
+ *    functions cannot fail; the shim falls back to the Go code on non-zero.
+ *  - Thread safety: every entry point may be called concurrently from many
+ *    threads (goroutines pinned to OS threads by cgo); each call borrows an
+ *    execution lane (CUDA stream + workspace) from a pool.
+ *  - Lists are sorted ascending uint64 (pb.List.Uids, protos/pb.proto:22-24).
+ *    Duplicates follow the reference: multiset-min for intersections,
+ *    multiset difference, global dedup for MergeSorted.
+ */
+#ifndef DGX_H
+#define DGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dgx_status {
+    DGX_OK = 0,
+    DGX_ERR_CUDA = -1,   /* a CUDA runtime call failed (dgx_last_error has the text) */
+    DGX_ERR_OOM = -2,    /* device or pinned-host allocation failed */
+    DGX_ERR_ARG = -3,    /* invalid argument */
+    DGX_ERR_CAP = -4,    /* out_cap too small for the result */
+    DGX_ERR_NODEV = -5   /* no CUDA device / library not initialised */
+} dgx_status;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Bind the library to CUDA device `device` (-1: current device).  Idempotent;
+ * called implicitly by the first host-pointer entry point. */
+int dgx_init(int device);
+void dgx_shutdown(void);
+/* Text of the last error on the calling thread ("" when none). */
+const char* dgx_last_error(void);
+/* Library / device description for logs: writes a NUL-terminated string. */
+int dgx_describe(char* buf, size_t buf_len);
+
+/* Pinned host memory: lists allocated here cross PCIe at full DMA speed. */
+void* dgx_host_alloc(size_t bytes);
+void dgx_host_free(void* p);
+
+/* Counters (metrics). */
+typedef struct dgx_stats {
+    uint64_t calls;
+    uint64_t uids_in;
+    uint64_t uids_out;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t kernel_launches;
+} dgx_stats;
+void dgx_get_stats(dgx_stats* out);
+
+/* ---- host-pointer entry points (what the cgo shim binds) ---------------- */
+
+/* algo.IntersectWith(u, v, o *pb.List)            algo/uidlist.go:142-167
+ * o.Uids = u ∩ v.  `out` may alias `u` (the in-place form every caller uses);
+ * `v` is never written.  out_cap >= min(n, m). */
+int dgx_intersect2(const uint64_t* u, size_t n, const uint64_t* v, size_t m,
+                   uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* algo.IntersectSorted(lists []*pb.List) *pb.List  algo/uidlist.go:297-329
+ * k == 0 -> length 0; k == 1 -> copy.  out_cap >= min_i lens[i]. */
+int dgx_intersect_sorted(const uint64_t* const* lists, const size_t* lens, size_t k,
+                         uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* algo.MergeSorted(lists []*pb.List) *pb.List      algo/uidlist.go:448-542
+ * Sorted union with global de-duplication.  NULL / empty lists are skipped.
+ * out_cap >= sum(lens). */
+int dgx_merge_sorted(const uint64_t* const* lists, const size_t* lens, size_t k,
+                     uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* algo.Difference(u, v *pb.List) *pb.List          algo/uidlist.go:332-362
+ * u \ v (multiset: one v consumes one equal u).  out_cap >= n. */
+int dgx_difference(const uint64_t* u, size_t n, const uint64_t* v, size_t m,
+                   uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* Batched independent 2-way intersections in CSR form: pair i intersects
+ * a[a_off[i]..a_off[i+1]) with b[b_off[i]..b_off[i+1]); results are written
+ * back to back into `out` with out_off[i]..out_off[i+1] (npairs+1 offsets).
+ * This is the handleUidPostings / updateUidMatrix shape
+ * (worker/task.go:783-987, query/query.go:1425-1438): N rows each filtered by
+ * algo.IntersectWith. */
+int dgx_intersect_batch(const uint64_t* a, const uint64_t* a_off,
+                        const uint64_t* b, const uint64_t* b_off, size_t npairs,
+                        uint64_t* out, uint64_t* out_off, size_t out_cap);
+
+/* pb.UidPack (protos/pb.proto:379-400) flattened to a struct of arrays.
+ * Block i: Base = base[i], NumUids = num_uids[i],
+ * Deltas = deltas[delta_off[i] .. delta_off[i+1]).  `deltas` need not be padded. */
+typedef struct dgx_pack_view {
+    uint32_t block_size;
+    size_t nblocks;
+    const uint64_t* base;
+    const uint32_t* num_uids;
+    const uint64_t* delta_off; /* nblocks + 1 entries, delta_off[0] == 0 */
+    const uint8_t* deltas;
+} dgx_pack_view;
+
+/* codec.Decode(pack *pb.UidPack, seek uint64) []uint64   codec/codec.go:444-452
+ * Decoder.Seek(seek, SeekStart) (:279-337) then every following block.
+ * out_cap >= ExactLen(pack) (codec/codec.go:427-440).  p == NULL is the nil pack. */
+int dgx_decode(const dgx_pack_view* p, uint64_t seek,
+               uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* codec.Decode followed by algo.IntersectSorted([decoded, lists...]) without
+ * the decoded list leaving the device (BASELINE config 3 pipeline). */
+int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek,
+                                const uint64_t* const* lists, const size_t* lens, size_t k,
+                                uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* ---- device-resident API ------------------------------------------------- */
+/* For callers that keep posting lists in HBM (a pack / list cache) and for
+ * roofline measurement.  All pointers named d_* are device pointers on the
+ * lane's device; they must be 16-byte aligned.  Calls are asynchronous on the
+ * lane's stream unless stated; dgx_lane_sync waits. */
+
+typedef struct dgx_lane dgx_lane; /* one CUDA stream + its workspace */
+
+/* stream: an existing cudaStream_t to run on (e.g. torch's current stream) or
+ * NULL to create a private non-blocking stream. */
+dgx_lane* dgx_lane_create(int device, void* stream);
+void dgx_lane_destroy(dgx_lane* lane);
+int dgx_lane_sync(dgx_lane* lane);
+void* dgx_lane_stream(dgx_lane* lane);
+/* Number of kernels this lane has launched so far. */
+uint64_t dgx_lane_launches(const dgx_lane* lane);
+
+void* dgx_dev_alloc(size_t bytes);
+void dgx_dev_free(void* d_ptr);
+int dgx_memcpy_h2d(dgx_lane* lane, void* d_dst, const void* h_src, size_t bytes);
+int dgx_memcpy_d2h(dgx_lane* lane, void* h_dst, const void* d_src, size_t bytes);
+
+typedef enum dgx_setop { DGX_OP_INTERSECT = 0, DGX_OP_DIFFERENCE = 1 } dgx_setop;
+
+/* Batched filter: query q keeps the values of its first list that are
+ * (INTERSECT) present in every other list of the query / (DIFFERENCE, exactly
+ * two lists) absent from the second.  Query q owns lists
+ * [k_off[q], k_off[q+1]) of d_lists/lens.  For INTERSECT the library drives
+ * from the shortest list, like IntersectSorted's length sort
+ * (algo/uidlist.go:309-311).  Results are concatenated in query order into
+ * d_out; d_out_off (nq + 1 device uint64) receives the CSR offsets.  If the
+ * total exceeds out_cap nothing beyond it is written and the following
+ * dgx_lane_sync returns DGX_ERR_CAP. */
+int dgx_dev_filter_batch(dgx_lane* lane, int op,
+                         const uint64_t* const* d_lists, const size_t* lens,
+                         const size_t* k_off, size_t nq,
+                         uint64_t* d_out, size_t out_cap, uint64_t* d_out_off);
+
+/* MergeSorted on device lists.  d_out_len: one device uint64. */
+int dgx_dev_merge_sorted(dgx_lane* lane, const uint64_t* const* d_lists, const size_t* lens, size_t k,
+                         uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
+
+/* A UidPack resident in HBM (deltas padded for 16-byte bulk copies, per-block
+ * output offsets precomputed). */
+typedef struct dgx_dev_pack dgx_dev_pack;
+int dgx_dev_pack_upload(dgx_lane* lane, const dgx_pack_view* p, dgx_dev_pack** out);
+void dgx_dev_pack_free(dgx_dev_pack* pk);
+size_t dgx_dev_pack_exact_len(const dgx_dev_pack* pk);  /* codec.ExactLen */
+size_t dgx_dev_pack_bytes(const dgx_dev_pack* pk);      /* bytes of the pack in HBM */
+/* Decode(pack, seek) into d_out; d_out_len: one device uint64. */
+int dgx_dev_decode(dgx_lane* lane, const dgx_dev_pack* pk, uint64_t seek,
+                   uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGX_H */
