@@ -60,6 +60,8 @@ static std::mutex g_mu;
 static int g_device = -1;
 static std::vector<dgx_lane*> g_pool;  // idle lanes for the host-pointer entry points
 static u32 g_stream_ratio = 16;
+static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's slice staging capacity
+constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 
 // ---------------------------------------------------------------------------
 // arenas
@@ -164,6 +166,12 @@ extern "C" int dgx_init(int device) {
         return fail(DGX_ERR_NODEV, "libdgx is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
     CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sizeof(DWarpSmem) * D_WARPS)));
+    CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(2 * F_TA * sizeof(u64) + kScapMax)));
+    if (const char* s = getenv("DGX_SCAP")) {
+        int v = atoi(s);
+        if (v >= 1024 && v <= (int)kScapMax) g_scap_override = (u32)v & ~15u;
+    }
     if (const char* s = getenv("DGX_STREAM_RATIO")) {
         int v = atoi(s);
         if (v >= 0) g_stream_ratio = (u32)v;
@@ -303,12 +311,13 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     FTask* ht = (FTask*)h_raw;
     FList* hl = (FList*)((char*)h_raw + tasks_b);
     uint64_t ntiles = 0, uids_in = 0;
-    size_t li = 0;
+    size_t li = 0, kmax = 1;
     std::vector<size_t> order;
     for (size_t q = 0; q < nq; ++q) {
         const size_t k0 = k_off[q], k1 = k_off[q + 1];
         const size_t k = k1 - k0;
         if (k == 0) return fail(DGX_ERR_ARG, "query %zu has no lists", q);
+        kmax = std::max(kmax, k);
         if (op == DGX_OP_DIFFERENCE && k != 2) return fail(DGX_ERR_ARG, "difference takes exactly two lists");
         order.resize(k);
         std::iota(order.begin(), order.end(), k0);
@@ -342,13 +351,16 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     P.ntiles = (u32)ntiles;
     P.op = op;
     P.stream_ratio = g_stream_ratio;
+    // staging capacity (bytes): ~1.1 tile-widths of 32-bit keys for every filter list of the widest query
+    P.scap_bytes = g_scap_override ? g_scap_override
+                                   : (u32)std::min<size_t>(32768, std::max<size_t>(kScapMin, (kmax - 1) * 1152 * 4));
     P.out = (u64*)d_out;
     P.out_cap = out_cap;
     P.out_off = (u64*)d_out_off;
     P.status = (u64*)d_status;
     P.ticket = (u32*)(d_status + ntiles * sizeof(u64));
     P.err = l->d_err;
-    filter_kernel<<<(unsigned)ntiles, F_NT, 0, l->stream>>>(P);
+    filter_kernel<<<(unsigned)ntiles, F_NT, 2 * F_TA * sizeof(u64) + P.scap_bytes, l->stream>>>(P);
     CK(cudaGetLastError());
     l->launches += 1;
     g_stats.launches += 1;

@@ -1,0 +1,118 @@
+"""Multi-GPU sharding of batches of independent set operations (pattern 1).
+
+The reference fans a batch of independent posting-list intersections over
+goroutines (x.DivideAndRule, worker/task.go:816-987); here the same batch is
+partitioned over the GPUs of one box, one process per GPU.  Units (pairs /
+queries) are independent, so there is NO data-path collective; the only exchange
+is the final result concatenation (an all-gatherv = all_gather of counts, then of
+payloads padded to the largest shard), done with torch.distributed (NCCL on GPUs,
+gloo in the CPU tests).
+
+This module is host logic only: which units a rank owns and how results are put
+back in unit order.  The compute step is passed in by the caller (libdgx on a
+GPU box).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+
+def lpt_partition(costs: Sequence[int], world: int) -> List[np.ndarray]:
+    """Longest-processing-time-first greedy partition of units by cost (bytes).
+
+    Returns, per rank, the sorted unit indices it owns.  Deterministic: ties go to
+    the lowest rank, units are visited in (cost desc, index asc) order.
+    """
+    costs = np.asarray(costs, dtype=np.int64)
+    order = np.lexsort((np.arange(costs.size), -costs))
+    load = np.zeros(world, dtype=np.int64)
+    owner = np.empty(costs.size, dtype=np.int64)
+    for u in order:
+        r = int(np.argmin(load))  # first minimum -> lowest rank on ties
+        owner[u] = r
+        load[r] += costs[u]
+    return [np.nonzero(owner == r)[0] for r in range(world)]
+
+
+def shard_offsets(counts: np.ndarray) -> np.ndarray:
+    out = np.zeros(counts.size + 1, dtype=np.int64)
+    np.cumsum(counts, out=out[1:])
+    return out
+
+
+def gatherv_results(dist, local_units: np.ndarray, local_out, local_off, n_units: int, device=None):
+    """All-gatherv of per-unit results.
+
+    local_units: global indices of the units this rank computed (ascending).
+    local_out:   torch int64 tensor, this rank's results concatenated in local unit order.
+    local_off:   torch int64 tensor (len(local_units)+1), CSR offsets into local_out.
+    Returns (out, off): torch tensors holding every unit's result in GLOBAL unit order
+    (identical on all ranks).
+    """
+    import torch
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    dev = local_out.device if device is None else device
+    # 1) per-unit lengths of every rank, padded to the largest shard (all_gather needs equal shapes)
+    n_local = torch.tensor([len(local_units)], dtype=torch.int64, device=dev)
+    n_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(n_all, n_local)
+    n_all = [int(t.item()) for t in n_all]
+    max_units = max(max(n_all), 1)
+    lens_local = torch.zeros(max_units, dtype=torch.int64, device=dev)
+    ids_local = torch.full((max_units,), -1, dtype=torch.int64, device=dev)
+    if len(local_units):
+        lens_local[: len(local_units)] = local_off[1:] - local_off[:-1]
+        ids_local[: len(local_units)] = torch.as_tensor(np.asarray(local_units), dtype=torch.int64, device=dev)
+    lens_all = [torch.zeros_like(lens_local) for _ in range(world)]
+    ids_all = [torch.zeros_like(ids_local) for _ in range(world)]
+    dist.all_gather(lens_all, lens_local)
+    dist.all_gather(ids_all, ids_local)
+    # 2) payloads, padded to the largest shard
+    tot_local = torch.tensor([int(local_off[-1].item()) if local_off.numel() else 0], dtype=torch.int64, device=dev)
+    tot_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(tot_all, tot_local)
+    tot_all = [int(t.item()) for t in tot_all]
+    max_tot = max(max(tot_all), 1)
+    pay_local = torch.zeros(max_tot, dtype=torch.int64, device=dev)
+    pay_local[: tot_all[rank]] = local_out[: tot_all[rank]]
+    pay_all = [torch.zeros_like(pay_local) for _ in range(world)]
+    dist.all_gather(pay_all, pay_local)
+    # 3) scatter back into global unit order
+    lens_g = torch.zeros(n_units, dtype=torch.int64, device=dev)
+    for r in range(world):
+        if n_all[r]:
+            lens_g[ids_all[r][: n_all[r]]] = lens_all[r][: n_all[r]]
+    off_g = torch.zeros(n_units + 1, dtype=torch.int64, device=dev)
+    off_g[1:] = torch.cumsum(lens_g, 0)
+    out_g = torch.zeros(max(int(off_g[-1].item()), 1), dtype=torch.int64, device=dev)
+    for r in range(world):
+        if n_all[r] == 0 or tot_all[r] == 0:
+            continue
+        ids = ids_all[r][: n_all[r]]
+        ln = lens_all[r][: n_all[r]]
+        src_off = torch.cumsum(ln, 0) - ln
+        dst_off = off_g[ids]
+        # element-wise destination index of every payload value of rank r
+        rep = torch.repeat_interleave(torch.arange(n_all[r], device=dev), ln)
+        within = torch.arange(tot_all[r], device=dev) - src_off[rep]
+        out_g[dst_off[rep] + within] = pay_all[r][: tot_all[r]]
+    return out_g[: int(off_g[-1].item())], off_g
+
+
+def run_sharded_pairs(dist, a_lists, b_lists, compute: Callable, device=None):
+    """Intersect pair i = (a_lists[i], b_lists[i]) for all i, sharded over the process group.
+
+    compute(units, a_lists, b_lists) -> (out int64 tensor, off int64 tensor) for the units a
+    rank owns (on a GPU box: one dgx_dev_filter_batch launch).  Returns results in pair order.
+    """
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    costs = [8 * (len(a) + len(b)) for a, b in zip(a_lists, b_lists)]
+    parts = lpt_partition(costs, world)
+    mine = parts[rank]
+    out, off = compute(mine, a_lists, b_lists)
+    return gatherv_results(dist, mine, out, off, len(a_lists), device=device)

@@ -1,0 +1,86 @@
+"""world_size-2 gloo test of the multi-GPU host logic (LPT partition + all-gatherv
+reassembly).  The compute step is stood in for by the oracle (this is a test of the
+sharding plumbing, not of the kernels)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(__file__))
+
+
+def test_lpt_partition_balanced_and_deterministic():
+    from dgraph_b200.shard import lpt_partition
+
+    rng = np.random.default_rng(0)
+    costs = rng.integers(1, 10**6, 1000)
+    for world in (1, 2, 4, 8):
+        parts = lpt_partition(costs, world)
+        allu = np.sort(np.concatenate(parts))
+        assert np.array_equal(allu, np.arange(1000))
+        loads = np.array([costs[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= costs.max()
+        parts2 = lpt_partition(costs, world)
+        assert all(np.array_equal(a, b) for a, b in zip(parts, parts2))
+    assert [p.tolist() for p in lpt_partition([5, 5, 5], 2)] == [[0, 2], [1]]
+    assert [p.tolist() for p in lpt_partition([], 2)] == [[], []]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import gen
+        from dgraph_b200.shard import run_sharded_pairs
+        from oracle import pyoracle as orc
+
+        rng = np.random.default_rng(42)  # same inputs on every rank
+        npairs = 37
+        A, B = [], []
+        for i in range(npairs):
+            n, m = int(rng.integers(0, 3000)), int(rng.integers(0, 5000))
+            master = gen.zipf_gaps(rng, 8000)
+            A.append(gen.thin(rng, master, n / 8000))
+            B.append(gen.thin(rng, master, m / 8000))
+
+        def compute(units, a_lists, b_lists):
+            outs = [orc.intersect_with(a_lists[u], b_lists[u]) for u in units]
+            off = np.zeros(len(units) + 1, dtype=np.int64)
+            if outs:
+                off[1:] = np.cumsum([o.size for o in outs])
+            cat = np.concatenate(outs + [np.zeros(0, np.uint64)]).view(np.int64)
+            return torch.from_numpy(cat.copy()), torch.from_numpy(off)
+
+        out, off = run_sharded_pairs(dist, A, B, compute)
+        out = out.numpy().view(np.uint64)
+        off = off.numpy()
+        ok = off.size == npairs + 1
+        for i in range(npairs):
+            ok = ok and np.array_equal(out[off[i]: off[i + 1]], orc.intersect_with(A[i], B[i]))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_pairs_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
