@@ -183,6 +183,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO would print to stdout before the JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     _lib.check(lib.dgx_init(local_rank))

@@ -136,12 +136,14 @@ constexpr u64 kValMask = (1ull << 62) - 1;
 // Called by one full warp.  Publishes this tile's aggregate, walks back to the
 // nearest inclusive prefix and publishes this tile's inclusive prefix.
 // Returns the exclusive prefix of the tile (same value in every lane).
+// kPublished: the tile's aggregate word has already been stored by someone else.
+template <bool kPublished = false>
 __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 aggregate, int lane) {
     if (tile == 0) {
         if (lane == 0) st_relaxed(status, kFlagPrefix | aggregate);
         return 0;
     }
-    if (lane == 0) st_relaxed(status + tile, kFlagAgg | aggregate);
+    if (!kPublished && lane == 0) st_relaxed(status + tile, kFlagAgg | aggregate);
     u64 exclusive = 0;
     long long idx = (long long)tile - 1;
     while (true) {

@@ -20,6 +20,7 @@
 
 #include "decode_kernel.cuh"
 #include "filter_kernel.cuh"
+#include "filter_pipe.cuh"
 #include "merge_kernel.cuh"
 
 using namespace dgx;
@@ -62,6 +63,10 @@ static std::vector<dgx_lane*> g_pool;  // idle lanes for the host-pointer entry 
 static u32 g_stream_ratio = 16;
 static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's slice staging capacity
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
+static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
+static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
+static int g_num_sms = 148;
+constexpr size_t kPipeSmemMax = 220 * 1024;
 
 // ---------------------------------------------------------------------------
 // arenas
@@ -88,13 +93,24 @@ struct DevArena {
         used += bytes;
         return DGX_OK;
     }
-    void reset() { used = 0; }
+    // Old chunks may still back pointers the current op hands to the host-side epilogue
+    // (e.g. the D2H copy after a lane sync), so they are freed in two steps: a lane sync
+    // makes them `freeable` (no queued work references them any more), the next op's
+    // reset() actually frees them.
+    std::vector<void*> freeable;
+    void reset() {
+        used = 0;
+        for (void* p : freeable) cudaFree(p);
+        freeable.clear();
+    }
     void release_retired() {
-        for (void* p : retired) cudaFree(p);
+        for (void* p : retired) freeable.push_back(p);
         retired.clear();
     }
     void destroy() {
         release_retired();
+        for (void* p : freeable) cudaFree(p);
+        freeable.clear();
         if (base) cudaFree(base);
         base = nullptr;
         cap = used = 0;
@@ -168,6 +184,10 @@ extern "C" int dgx_init(int device) {
                             (int)(sizeof(DWarpSmem) * D_WARPS)));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * F_TA * sizeof(u64) + kScapMax)));
+    CK(cudaFuncSetAttribute(filter_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
+    g_num_sms = prop.multiProcessorCount;
+    if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
+    if (const char* s = getenv("DGX_PIPE_MIN_K")) g_pipe_min_k = (size_t)std::max(1, atoi(s));
     if (const char* s = getenv("DGX_SCAP")) {
         int v = atoi(s);
         if (v >= 1024 && v <= (int)kScapMax) g_scap_override = (u32)v & ~15u;
@@ -312,6 +332,9 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     FList* hl = (FList*)((char*)h_raw + tasks_b);
     uint64_t ntiles = 0, uids_in = 0;
     size_t li = 0, kmax = 1;
+    for (size_t q = 0; q < nq; ++q) kmax = std::max(kmax, k_off[q + 1] - k_off[q]);
+    const bool use_pipe = g_filter_pipe && kmax >= g_pipe_min_k;
+    const uint64_t tile_sz = use_pipe ? P_TA : F_TA;
     std::vector<size_t> order;
     for (size_t q = 0; q < nq; ++q) {
         const size_t k0 = k_off[q], k1 = k_off[q + 1];
@@ -335,7 +358,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
             ++li;
         }
         const uint64_t lenA = lists[order[0]].len;
-        ntiles += std::max<uint64_t>(1, (lenA + F_TA - 1) / F_TA);
+        ntiles += std::max<uint64_t>(1, (lenA + tile_sz - 1) / tile_sz);
     }
     if (ntiles > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large (%llu tiles)", (unsigned long long)ntiles);
     const size_t status_b = ntiles * sizeof(u64) + 64;
@@ -360,10 +383,68 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     P.status = (u64*)d_status;
     P.ticket = (u32*)(d_status + ntiles * sizeof(u64));
     P.err = l->d_err;
-    filter_kernel<<<(unsigned)ntiles, F_NT, 2 * F_TA * sizeof(u64) + P.scap_bytes, l->stream>>>(P);
-    CK(cudaGetLastError());
-    l->launches += 1;
-    g_stats.launches += 1;
+    if (!use_pipe) {
+        filter_kernel<<<(unsigned)ntiles, F_NT, 2 * F_TA * sizeof(u64) + P.scap_bytes, l->stream>>>(P);
+        CK(cudaGetLastError());
+        l->launches += 1;
+        g_stats.launches += 1;
+    } else {
+        // ---- persistent TMA pipeline: plan pre-pass + filter_pipe_kernel ----------------
+        void* hp_raw;
+        rc = l->host.alloc(nq * sizeof(u64), &hp_raw);
+        if (rc) return rc;
+        u64* h_pb = (u64*)hp_raw;
+        u64 npairs = 0;
+        for (size_t q = 0; q < nq; ++q) {
+            h_pb[q] = npairs;
+            const u64 nt = (q + 1 < nq ? ht[q + 1].tile_base : ntiles) - ht[q].tile_base;
+            npairs += nt * (u64)(ht[q].k - 1);
+        }
+        void *d_pb, *d_plan, *d_tiles;
+        rc = l->ws.alloc(nq * sizeof(u64), &d_pb);
+        if (rc) return rc;
+        rc = l->ws.alloc(ntiles * sizeof(PTileEntry), &d_tiles);
+        if (rc) return rc;
+        rc = l->ws.alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, l->stream));
+        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
+                                                                                      P.ntiles, (PTileEntry*)d_tiles);
+        CK(cudaGetLastError());
+        l->launches += 1;
+        g_stats.launches += 1;
+        if (npairs) {
+            const u64 blocks = (npairs + 255) / 256;
+            if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
+            filter_plan_kernel<<<(unsigned)blocks, 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
+                                                                         (PPlanEntry*)d_plan);
+            CK(cudaGetLastError());
+            l->launches += 1;
+            g_stats.launches += 1;
+        }
+        PParams PP;
+        PP.f = P;
+        PP.plan_base = (const u64*)d_pb;
+        PP.plan = (const PPlanEntry*)d_plan;
+        PP.tiles = (const PTileEntry*)d_tiles;
+        const size_t nl = std::min<size_t>(std::max<size_t>(kmax - 1, 1), P_MAXL);
+        size_t cap = (P_TA + P_TA / 8) * nl * (kmax <= 2 ? 4 : 1);
+        if (g_scap_override) cap = g_scap_override / 8;
+        cap = std::min<size_t>(std::max<size_t>(cap, P_TA + P_TA / 8), 9216) & ~size_t(1);
+        PP.slice_cap = (u32)cap;
+        const size_t smem = ((sizeof(PShared) + 127) & ~size_t(127)) + (1 + P_OS) * P_TA * sizeof(u64) +
+                            2 * ((P_TA + 2) + cap) * sizeof(u64);
+        if (smem > kPipeSmemMax) return fail(DGX_ERR_ARG, "pipeline stage too large");
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pipe_kernel, P_NT, smem));
+        if (per_sm < 1) return fail(DGX_ERR_CUDA, "filter_pipe_kernel does not fit on an SM");
+        const u64 resident = (u64)per_sm * (u64)g_num_sms;
+        PP.nctas = (u32)std::min<u64>(resident, ntiles);
+        filter_pipe_kernel<<<PP.nctas, P_NT, smem, l->stream>>>(PP);
+        CK(cudaGetLastError());
+        l->launches += 1;
+        g_stats.launches += 1;
+    }
     g_stats.uids_in += uids_in;
     return DGX_OK;
 }

@@ -1,0 +1,584 @@
+// filter_pipe.cuh -- persistent, TMA-fed version of the batched sorted-set filter.
+//
+// Same contract as filter_kernel.cuh (IntersectWith / IntersectSorted chain /
+// Difference over a batch of queries, bit-exact incl. duplicate semantics), built
+// as a Blackwell pipeline:
+//
+//   filter_plan_kernel   one warp per (tile, filter list): both slice bounds
+//                        [lower_bound(L_j, tile first), upper_bound(L_j, tile last))
+//                        with interleaved 32-ary searches -> a small plan in HBM.
+//   filter_pipe_kernel   persistent CTAs (grid = resident capacity).  Warp roles:
+//     M  (1 warp)  metadata: claims the next tile (atomic ticket = look-back order),
+//                  resolves its task, list descriptors and plan entries and pushes a
+//                  tile descriptor into a small ring in shared memory;
+//     T  (1 warp)  waits for a free stage, lays the tile's slices out and issues ONE
+//                  TMA bulk copy (cp.async.bulk, mbarrier complete_tx) per list plus
+//                  one for the 1024 driving values: global -> shared with no
+//                  register staging and no consumer instruction spent on loads;
+//     C (16 warps) consume a stage, each warp on its own 64 candidates (2 rows in
+//                  registers) and with NO block barrier: binary-lifting searches over
+//                  the staged 64-bit keys, interleaved across rows / lists for ILP,
+//                  warp-level re-packs between lists, survivors dropped into the
+//                  warp's fixed segment of an output slot;
+//     O  (1 warp)  drains output slots: tile count -> decoupled look-back -> ordered
+//                  stores.  Only this warp ever waits on other CTAs.
+//   Two stages and two output slots are in flight per CTA, so the TMA traffic of
+//   tile i+1 and the look-back of tile i-1 overlap the searches of tile i.
+//
+// Lists that are not pre-staged (slice larger than the stage, or more than 8
+// filter lists) are binary-searched in HBM by the surviving candidates.
+#pragma once
+
+#include "decode_kernel.cuh"   // mbarrier / TMA helpers
+#include "filter_kernel.cuh"
+
+namespace dgx {
+
+constexpr int P_CW = 8;                  // consumer warps
+constexpr int P_CT = P_CW * 32;          // consumer threads
+constexpr int P_NT = P_CT + 96;          // + metadata warp + TMA warp + output warp
+constexpr int P_VA = 2;                  // candidate rows per consumer warp
+constexpr int P_WC = 32 * P_VA;          // candidates per consumer warp
+constexpr int P_TA = P_CW * 64;          // candidates per tile
+constexpr int P_OS = 4;                  // output slots in flight
+constexpr int P_MAXL = 8;                // filter lists a stage can hold
+constexpr int P_RING = 4;                // tile descriptors in flight between M and T
+constexpr u32 P_END = 0xffffffffu;
+static_assert(P_CW * P_WC == P_TA, "tile geometry");
+
+struct PPlanEntry { u64 r0, r1; };
+struct PTileEntry {            // everything the metadata warp needs about a tile, resolved by filter_tiles_kernel
+    u32 task, list_first, k, na;
+    u64 a0, plan_idx, prev;
+    u32 has_prev, pad;
+};
+
+struct PParams {
+    FParams f;                 // tasks, lists, op, outputs, look-back state (ticket unused)
+    const u64* plan_base;      // per task: index of its first plan entry
+    const PPlanEntry* plan;    // per (tile, filter list)
+    const struct PTileEntry* tiles;  // per tile
+    u32 slice_cap;             // stage capacity for slices, in u64 values
+    u32 nctas;
+};
+
+// ---- plan ---------------------------------------------------------------------------
+// One THREAD per (tile, filter list): r0 = first i with L[i] >= tile first, r1 = first i
+// with L[i] > tile last, as two interleaved binary searches.  A binary search touches one
+// new 32-byte sector per level only near its end (~8 sectors), where the 32-ary warp
+// search of filter_kernel.cuh touches ~70: the plan must not cost a second pass over HBM.
+__global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
+                                                          const u64* __restrict__ plan_base, u32 ntasks, u64 npairs,
+                                                          PPlanEntry* __restrict__ plan) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    u32 lo = 0, hi = ntasks;  // last task with plan_base <= p (the one that owns pair p)
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (plan_base[mid] <= p) lo = mid; else hi = mid;
+    }
+    const FTask T = tasks[lo];
+    const u64 local = p - plan_base[lo];
+    const u32 km1 = T.k - 1;
+    const u64 tl = local / km1;
+    const u32 j = (u32)(local - tl * km1) + 1;
+    const FList LA = lists[T.list_first];
+    const u64 lenA = flist_len(LA);
+    const u64 a0 = tl * P_TA;
+    u64 r0 = 0, r1 = 0;
+    if (a0 < lenA) {
+        const u64 na = lenA - a0 < (u64)P_TA ? lenA - a0 : (u64)P_TA;
+        const u64 tlo = ld_probe(LA.ptr + a0), thi = ld_probe(LA.ptr + a0 + na - 1);
+        const FList Lj = lists[T.list_first + j];
+        const u64* __restrict__ B = Lj.ptr;
+        u64 l0 = 0, h0 = flist_len(Lj), l1 = 0, h1 = h0;
+        while (l0 < h0 || l1 < h1) {
+            const u64 m0 = l0 + ((h0 - l0) >> 1), m1 = l1 + ((h1 - l1) >> 1);
+            const bool a = l0 < h0, c = l1 < h1;
+            const u64 v0 = a ? ld_probe(B + m0) : 0, v1 = c ? ld_probe(B + m1) : 0;
+            if (a) { if (v0 < tlo) l0 = m0 + 1; else h0 = m0; }
+            if (c) { if (v1 <= thi) l1 = m1 + 1; else h1 = m1; }
+        }
+        r0 = l0; r1 = l1;
+    }
+    plan[p].r0 = r0;
+    plan[p].r1 = r1;
+}
+
+// One thread per tile: which task it belongs to and where its driving values start.
+__global__ void __launch_bounds__(256) filter_tiles_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
+                                                           const u64* __restrict__ plan_base, u32 ntasks, u32 ntiles,
+                                                           PTileEntry* __restrict__ tiles) {
+    const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
+    u32 lo = 0, hi = ntasks;
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (tasks[mid].tile_base <= (u64)tile) lo = mid; else hi = mid;
+    }
+    const FTask T = tasks[lo];
+    const FList LA = lists[T.list_first];
+    const u64 lenA = flist_len(LA);
+    PTileEntry e;
+    e.task = lo; e.list_first = T.list_first; e.k = T.k;
+    e.a0 = ((u64)tile - T.tile_base) * P_TA;
+    e.na = e.a0 < lenA ? (u32)((lenA - e.a0 < (u64)P_TA) ? (lenA - e.a0) : (u64)P_TA) : 0u;
+    e.plan_idx = plan_base[lo] + ((u64)tile - T.tile_base) * (u64)(T.k - 1);
+    e.has_prev = (e.a0 > 0 && e.na > 0) ? 1u : 0u;
+    e.prev = e.has_prev ? ld_probe(LA.ptr + e.a0 - 1) : 0;
+    e.pad = 0;
+    tiles[tile] = e;
+}
+
+// ---- pipeline state in shared memory -------------------------------------------------
+struct PDesc {                 // one tile, produced by M, consumed by T
+    u32 tile, task, na, k, list_first, has_prev;
+    u64 a0, prev, plan_idx;
+    const u64* A;
+    const u64* ptr[P_MAXL];
+    u64 len[P_MAXL], r0[P_MAXL], r1[P_MAXL];
+};
+struct PStageInfo {            // one stage, produced by T, consumed by C
+    u32 tile, task, na, k, list_first, has_prev, nstaged, headA;
+    u64 a0, prev, plan_idx;
+    const u64* A;
+    const u64* ptr[P_MAXL];
+    u64 len[P_MAXL], r0[P_MAXL];
+    u32 off[P_MAXL], n[P_MAXL];
+};
+struct POutSlot {              // survivors of one tile: warp w owns data[P_WC*w ..) and cnt[w]
+    u32 tile, task;
+    u32 total, arrived;        // running sum of cnt / number of warps that delivered (reset by O)
+    u32 cnt[P_CW];
+};
+struct PShared {
+    u64 full[2], empty[2], ofull[P_OS], oempty[P_OS], ready[P_RING], freed[P_RING];
+    PDesc ring[P_RING];
+    PStageInfo st[2];
+    POutSlot os[P_OS];
+};
+
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Re-pack a consumer warp's survivors into rows 0..ceil(live/32)-1 (order preserved).
+__device__ __forceinline__ void pwarp_repack(u64 (&c)[P_VA], unsigned& alive, int& rows, u64* s_w, int lane) {
+    unsigned b[P_VA];
+    int tot = 0;
+#pragma unroll
+    for (int i = 0; i < P_VA; ++i) {
+        b[i] = __ballot_sync(0xffffffffu, (i < rows) && ((alive >> i) & 1u));
+        tot += __popc(b[i]);
+    }
+    const int nrows = (tot + 31) >> 5;
+    if (nrows >= rows) return;
+    if (nrows == 0) { rows = 0; alive = 0; return; }
+    const unsigned lt = (1u << lane) - 1u;
+    int before = 0;
+#pragma unroll
+    for (int i = 0; i < P_VA; ++i) {
+        if ((b[i] >> lane) & 1u) s_w[before + __popc(b[i] & lt)] = c[i];
+        before += __popc(b[i]);
+    }
+    __syncwarp();
+    alive = 0;
+#pragma unroll
+    for (int i = 0; i < P_VA; ++i) {
+        if (i < nrows && 32 * i + lane < tot) { c[i] = s_w[32 * i + lane]; alive |= 1u << i; }
+    }
+    __syncwarp();
+    rows = nrows;
+}
+
+struct PTile {          // per-thread constants of the tile being consumed
+    const u64* cand;    // staged driving values (tile order)
+    const u64* A;
+    u64 a0, prev;
+    bool has_prev;
+    int cidx0;
+    int op;
+};
+
+// NJ independent lower-bound searches advanced in lock step (binary lifting): job j
+// looks for x[j] in sb[j][0..n[j]).  The ladder starts at the largest power of two
+// <= max n, every step is guarded by t <= n[j], so the NJ dependent chains overlap.
+template <int NJ>
+__device__ __forceinline__ void lift_multi(const u64* const (&sb)[NJ], const int (&n)[NJ], const u64 (&x)[NJ],
+                                           int (&pos)[NJ]) {
+    int nmax = 1;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { pos[j] = 0; nmax = n[j] > nmax ? n[j] : nmax; }
+#define DGX_LIFTM(H)                                                              \
+    {                                                                             \
+        _Pragma("unroll") for (int j = 0; j < NJ; ++j) {                          \
+            const int t_ = pos[j] + (H);                                          \
+            if (t_ <= n[j] && sb[j][t_ - 1] < x[j]) pos[j] = t_;                  \
+        }                                                                         \
+    }
+    switch (31 - __clz(nmax)) {
+        case 14: DGX_LIFTM(16384)
+        case 13: DGX_LIFTM(8192)
+        case 12: DGX_LIFTM(4096)
+        case 11: DGX_LIFTM(2048)
+        case 10: DGX_LIFTM(1024)
+        case 9: DGX_LIFTM(512)
+        case 8: DGX_LIFTM(256)
+        case 7: DGX_LIFTM(128)
+        case 6: DGX_LIFTM(64)
+        case 5: DGX_LIFTM(32)
+        case 4: DGX_LIFTM(16)
+        case 3: DGX_LIFTM(8)
+        case 2: DGX_LIFTM(4)
+        case 1: DGX_LIFTM(2)
+        default: DGX_LIFTM(1)
+    }
+#undef DGX_LIFTM
+}
+
+// hit test of candidate value x (row i of this lane) at staged position p of list (sb, n, g0, B, lenB)
+__device__ __forceinline__ bool phit(const PTile& X, u64 x, int i, unsigned dup, const u64* sb, int n, int p, u64 g0,
+                                     const u64* __restrict__ B, u64 lenB) {
+    if (!((dup >> i) & 1u)) return (p < n) && (sb[p] == x);
+    const u64 g = g0 + (u64)p + cand_rank(X.cand, X.cidx0 + 32 * i, x, X.has_prev, X.prev, X.A, X.a0);
+    return (g < lenB) && (ld_probe(B + g) == x);
+}
+
+__global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) {
+    extern __shared__ __align__(128) unsigned char p_smem[];
+    const FParams& P = PP.f;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 scap = PP.slice_cap;
+    // layout: [PShared | s_work P_TA | out slots P_OS x P_TA | stage0: A (P_TA+2) | slices scap | stage1: ...]
+    PShared& S = *reinterpret_cast<PShared*>(p_smem);
+    u64* s_work = reinterpret_cast<u64*>(p_smem + ((sizeof(PShared) + 127) & ~size_t(127)));
+    u64* s_out = s_work + P_TA;  // P_OS slots of P_TA values
+    u64* stage_mem = s_work + (1 + P_OS) * P_TA;
+    const size_t stage_words = (size_t)(P_TA + 2) + scap;
+    u64* s_A[2] = {stage_mem, stage_mem + stage_words};
+    u64* s_SL[2] = {stage_mem + (P_TA + 2), stage_mem + stage_words + (P_TA + 2)};
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), P_CW); }
+        for (int s = 0; s < P_OS; ++s) { mbar_init(smem_u32(&S.ofull[s]), P_CW); mbar_init(smem_u32(&S.oempty[s]), 1); }
+        for (int r = 0; r < P_RING; ++r) { mbar_init(smem_u32(&S.ready[r]), 1); mbar_init(smem_u32(&S.freed[r]), 1); }
+        for (int s = 0; s < P_OS; ++s) { S.os[s].total = 0; S.os[s].arrived = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+
+    if (wid == P_CW) {
+        // =========================== M: metadata warp ===============================
+        // Two tiles per iteration (one per half-warp), claimed with ONE atomic so a CTA's
+        // tiles stay in look-back order; the ticket for the next iteration is fetched
+        // before this iteration's loads, so the chain per tile pair is two global
+        // latencies: tile table -> {list descriptors, plan entries}.  Sub-lane u < 8 of a
+        // half-warp resolves filter list u of its tile.
+        const int h = lane >> 4, u = lane & 15;
+        u32 next_base = 0;
+        if (lane == 0) next_base = atomicAdd(P.ticket, 2u);
+        for (u32 itn = 0;; ++itn) {
+            const u32 seq = 2 * itn + h;
+            const u32 slot = seq % P_RING, use = seq / P_RING;
+            const u32 base_ticket = __shfl_sync(0xffffffffu, next_base, 0);
+            if (lane == 0) next_base = atomicAdd(P.ticket, 2u);  // prefetch (harmless past the end)
+            if (u == 0) mbar_wait(smem_u32(&S.freed[slot]), (use & 1u) ^ 1u);
+            __syncwarp();
+            const u64 tile64 = (u64)base_ticket + h;
+            const bool valid = tile64 < (u64)P.ntiles;
+            const u32 tile = valid ? (u32)tile64 : P_END;
+            PTileEntry e;
+            e.task = 0; e.list_first = 0; e.k = 0; e.na = 0; e.a0 = 0; e.plan_idx = 0; e.prev = 0; e.has_prev = 0;
+            if (valid) e = PP.tiles[tile];
+            u64 r0 = 0, r1 = 0, lenj = 0;
+            const u64* ptrj = nullptr;
+            const u64* A = nullptr;
+            if (valid) {
+                if (u < P_MAXL && (u32)u + 1 < e.k) {
+                    const FList Lj = P.lists[e.list_first + 1 + u];
+                    ptrj = Lj.ptr;
+                    lenj = flist_len(Lj);
+                    const PPlanEntry pe = PP.plan[e.plan_idx + u];
+                    r0 = pe.r0; r1 = pe.r1;
+                }
+                if (u == 0) A = P.lists[e.list_first].ptr;
+            }
+            PDesc& D = S.ring[slot];
+            if (u == 0) {
+                D.tile = tile; D.task = e.task; D.na = e.na; D.k = e.k; D.list_first = e.list_first;
+                D.has_prev = e.has_prev; D.a0 = e.a0; D.prev = e.prev; D.plan_idx = e.plan_idx; D.A = A;
+            }
+            if (u < P_MAXL) { D.ptr[u] = ptrj; D.len[u] = lenj; D.r0[u] = r0; D.r1[u] = r1; }
+            __syncwarp();
+            if (u == 0) mbar_arrive(smem_u32(&S.ready[slot]));
+            if (__ballot_sync(0xffffffffu, !valid)) break;  // an END descriptor was published
+        }
+    } else if (wid == P_CW + 1) {
+        // =========================== T: TMA warp ====================================
+        for (u32 seq = 0;; ++seq) {
+            const u32 slot = seq % P_RING, use = seq / P_RING;
+            mbar_wait(smem_u32(&S.ready[slot]), use & 1u);
+            const PDesc& D = S.ring[slot];
+            const u32 st = seq & 1u, suse = seq >> 1;
+            mbar_wait(smem_u32(&S.empty[st]), (suse & 1u) ^ 1u);
+            PStageInfo& G = S.st[st];
+            const u32 tile = D.tile;
+            if (tile == P_END) {
+                if (lane == 0) { G.tile = P_END; mbar_arrive(smem_u32(&S.full[st])); }
+                break;
+            }
+            // layout of the staged slices: lane t owns filter list t
+            const u32 km1 = D.k - 1;
+            const bool mine = (u32)lane < km1 && lane < P_MAXL;
+            u64 n64 = 0;
+            const u64* src = nullptr;
+            u32 head = 0;
+            if (mine) {
+                n64 = D.r1[lane] - D.r0[lane];
+                src = D.ptr[lane] + D.r0[lane];
+                head = (u32)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
+            }
+            const u32 words = (mine && n64 <= (u64)scap) ? (u32)((n64 + head + 1) & ~1ull) : 0u;  // 16-byte granules
+            u32 incl = words;
+#pragma unroll
+            for (int dlt = 1; dlt < 8; dlt <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, incl, dlt);
+                if (lane >= dlt) incl += v;
+            }
+            const bool fits = mine && n64 <= (u64)scap && incl <= scap;
+            const unsigned fm = __ballot_sync(0xffffffffu, fits);
+            u32 nstaged = (u32)(__ffs(~fm) - 1);  // leading run of lists that fit
+            if (nstaged > km1) nstaged = km1;
+            if (nstaged > P_MAXL) nstaged = P_MAXL;
+            const u32 na = D.na;
+            const u32 headA = na ? (u32)((reinterpret_cast<uintptr_t>(D.A + D.a0) >> 3) & 1) : 0u;
+            const u32 bytesA = na ? (u32)(((na + headA + 1) & ~1u) * 8u) : 0u;
+            const u32 my_bytes = ((u32)lane < nstaged) ? words * 8u : 0u;
+            u32 tot = my_bytes;
+#pragma unroll
+            for (int dlt = 16; dlt > 0; dlt >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dlt);
+            tot += bytesA;
+            if (lane < P_MAXL) {
+                G.ptr[lane] = D.ptr[lane]; G.len[lane] = D.len[lane]; G.r0[lane] = D.r0[lane];
+                G.off[lane] = incl - words + head; G.n[lane] = (u32)(n64 < 0xffffffffull ? n64 : 0xffffffffull);
+            }
+            if (lane == 0) {
+                G.tile = tile; G.task = D.task; G.na = na; G.k = D.k; G.list_first = D.list_first;
+                G.has_prev = D.has_prev; G.nstaged = nstaged; G.headA = headA;
+                G.a0 = D.a0; G.prev = D.prev; G.plan_idx = D.plan_idx; G.A = D.A;
+            }
+            __syncwarp();
+            const u32 bar = smem_u32(&S.full[st]);
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (tot) mbar_expect_tx(bar, tot); else mbar_arrive(bar);
+                if (bytesA) tma_bulk_g2s(smem_u32(s_A[st]), D.A + D.a0 - headA, bytesA, bar);
+            }
+            __syncwarp();
+            if (my_bytes) tma_bulk_g2s(smem_u32(s_SL[st] + (incl - words)), src - head, my_bytes, bar);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.freed[slot]));  // descriptor consumed
+        }
+    } else if (wid == P_CW + 2) {
+        // =========================== O: output warp =================================
+        for (u32 it = 0;; ++it) {
+            const u32 sl = it % P_OS, use = it / P_OS;
+            mbar_wait(smem_u32(&S.ofull[sl]), use & 1u);
+            const POutSlot& O = S.os[sl];
+            const u32 tile = O.tile;
+            if (tile == P_END) break;
+            const u32 q = O.task;
+            u32 cw = lane < P_CW ? O.cnt[lane] : 0u;
+            u32 incl = cw;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, incl, dlt);
+                if (lane >= dlt) incl += v;
+            }
+            const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+            const u64 base = lookback_exclusive<true>(P.status, tile, (u64)total, lane);
+            if (lane == 0) {
+                if ((u64)tile == P.tasks[q].tile_base) P.out_off[q] = base;
+                if (tile == P.ntiles - 1) P.out_off[P.ntasks] = base + (u64)total;
+            }
+            if (base + (u64)total > P.out_cap) {
+                if (lane == 0) atomicExch(P.err, 1);
+            } else {
+                const u64* data = s_out + (size_t)sl * P_TA;
+#pragma unroll 1
+                for (int w = 0; w < P_CW; ++w) {
+                    const u32 nw = __shfl_sync(0xffffffffu, cw, w);
+                    const u32 ow = __shfl_sync(0xffffffffu, incl, w) - nw;
+                    for (u32 i = lane; i < nw; i += 32) st_stream(P.out + base + ow + i, data[P_WC * w + i]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                S.os[sl].total = 0;
+                S.os[sl].arrived = 0;
+                mbar_arrive(smem_u32(&S.oempty[sl]));
+            }
+        }
+    } else {
+        // =========================== C: consumer warps ==============================
+        u64* s_w = s_work + P_WC * wid;
+        for (u32 it = 0;; ++it) {
+            const u32 st = it & 1u, suse = it >> 1;
+            mbar_wait(smem_u32(&S.full[st]), suse & 1u);
+            const PStageInfo& G = S.st[st];
+            const u32 tile = G.tile;
+            const u32 osl = it % P_OS, ouse = it / P_OS;
+            POutSlot& O = S.os[osl];
+            if (tile == P_END) {
+                mbar_wait(smem_u32(&S.oempty[osl]), (ouse & 1u) ^ 1u);
+                if (wid == 0 && lane == 0) O.tile = P_END;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&S.ofull[osl]));
+                break;
+            }
+            const u32 na = G.na, k = G.k, q = G.task;
+            const u64* cand = s_A[st] + G.headA;
+            const u64* sl = s_SL[st];
+            PTile X;
+            X.cand = cand; X.A = G.A; X.a0 = G.a0; X.prev = G.prev; X.has_prev = G.has_prev != 0;
+            X.cidx0 = P_WC * wid + lane; X.op = P.op;
+
+            u64 c[P_VA] = {0, 0};
+            unsigned alive = 0, dup = 0;
+            int rows;
+            {
+                const int wn = (int)na - P_WC * wid;
+                rows = wn <= 0 ? 0 : (wn >= P_WC ? P_VA : (wn + 31) >> 5);
+#pragma unroll
+                for (int i = 0; i < P_VA; ++i) {
+                    const int idx = X.cidx0 + 32 * i;
+                    if (idx < (int)na) {
+                        c[i] = cand[idx];
+                        alive |= 1u << i;
+                        const u64 before = idx > 0 ? cand[idx - 1] : X.prev;
+                        if ((idx > 0 || X.has_prev) && before == c[i]) dup |= 1u << i;
+                    }
+                }
+            }
+            const bool warp_dup = __any_sync(0xffffffffu, dup != 0);  // repeated values: candidates stay in place
+            const u32 km1 = (k > 1) ? k - 1 : 0u;
+            const u32 nstaged = G.nstaged < km1 ? G.nstaged : km1;
+
+            u32 t = 0;
+            while (t < km1 && rows > 0) {
+                if (t < nstaged) {
+                    if (rows == 2 || t + 1 >= nstaged) {
+                        // ---- one staged list, the warp's rows interleaved --------------------
+                        const int n = (int)G.n[t];
+                        if (n == 0) {
+                            if (P.op == 0) { alive = 0; rows = 0; }
+                        } else {
+                            const u64* sb = sl + G.off[t];
+                            const u64* const sbs[2] = {sb, sb};
+                            const int ns[2] = {n, n};
+                            const u64 xs[2] = {c[0], c[1]};
+                            int pos[2];
+                            lift_multi<2>(sbs, ns, xs, pos);
+#pragma unroll
+                            for (int i = 0; i < P_VA; ++i)
+                                if ((alive >> i) & 1u) {
+                                    const bool h = phit(X, c[i], i, dup, sb, n, pos[i], G.r0[t], G.ptr[t], G.len[t]);
+                                    if ((P.op == 0) != h) alive &= ~(1u << i);
+                                }
+                        }
+                        t += 1;
+                    } else {
+                        // ---- single row: up to three staged lists interleaved ---------------
+                        const u32 nl = (nstaged - t >= 3) ? 3u : 2u;
+                        const u64* sbs[3];
+                        int ns[3];
+                        u64 xs[3];
+                        int pos[3];
+                        bool empty_list = false;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const u32 tj = (u32)j < nl ? t + j : t;
+                            sbs[j] = sl + G.off[tj];
+                            ns[j] = (int)G.n[tj];
+                            xs[j] = c[0];
+                            if ((u32)j < nl && ns[j] == 0) empty_list = true;
+                            if (ns[j] == 0) { ns[j] = 1; sbs[j] = cand; }  // harmless dummy search
+                        }
+                        const u64* const (&sbr)[3] = sbs;
+                        lift_multi<3>(sbr, ns, xs, pos);
+                        if (empty_list && P.op == 0) {
+                            alive = 0; rows = 0;
+                        } else if (alive & 1u) {
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                if ((u32)j < nl && (alive & 1u) && (int)G.n[t + j] > 0) {
+                                    const bool h = phit(X, c[0], 0, dup, sbs[j], (int)G.n[t + j], pos[j], G.r0[t + j],
+                                                        G.ptr[t + j], G.len[t + j]);
+                                    if ((P.op == 0) != h) alive &= ~1u;
+                                }
+                        }
+                        t += nl;
+                    }
+                } else {
+                    // ---- list not staged: live candidates binary-search it in HBM -----------
+                    const FList Lj = P.lists[G.list_first + 1 + t];
+                    const u64* __restrict__ B = Lj.ptr;
+                    const u64 lenB = flist_len(Lj);
+                    const PPlanEntry e = PP.plan[G.plan_idx + t];
+                    const u64 sz = e.r1 - e.r0;
+#pragma unroll
+                    for (int i = 0; i < P_VA; ++i) {
+                        if ((alive >> i) & 1u) {
+                            const u64 x = c[i];
+                            u64 gpos = e.r0 + (sz ? lower_bound_g(B + e.r0, sz, x) : 0);
+                            if ((dup >> i) & 1u) gpos += cand_rank(cand, X.cidx0 + 32 * i, x, X.has_prev, X.prev, X.A, X.a0);
+                            const bool h = (gpos < lenB) && (ld_probe(B + gpos) == x);
+                            if ((P.op == 0) != h) alive &= ~(1u << i);
+                        }
+                    }
+                    t += 1;
+                }
+                if (t < km1) {
+                    if (!warp_dup) pwarp_repack(c, alive, rows, s_w, lane);
+                    else if (!__any_sync(0xffffffffu, alive != 0)) rows = 0;
+                }
+            }
+            if (rows == 0) alive = 0;
+
+            // ---- this warp is done with the stage: hand it back to T ---------------------------
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.empty[st]));
+
+            // ---- survivors -> this warp's segment of the output slot -----------------------------
+            mbar_wait(smem_u32(&S.oempty[osl]), (ouse & 1u) ^ 1u);
+            {
+                u64* od = s_out + (size_t)osl * P_TA + P_WC * wid;
+                const unsigned lt = (1u << lane) - 1u;
+                int before = 0;
+#pragma unroll
+                for (int i = 0; i < P_VA; ++i) {
+                    const unsigned bo = __ballot_sync(0xffffffffu, (alive >> i) & 1u);
+                    if ((bo >> lane) & 1u) od[before + __popc(bo & lt)] = c[i];
+                    before += __popc(bo);
+                }
+                if (lane == 0) {
+                    O.cnt[wid] = (u32)before;
+                    if (wid == 0) { O.tile = tile; O.task = q; }
+                    // The last warp to deliver publishes the tile's aggregate for the look-back
+                    // right away: successors never wait for this CTA's output warp to get here.
+                    atomicAdd(&O.total, (u32)before);
+                    __threadfence_block();
+                    if (atomicAdd(&O.arrived, 1u) == P_CW - 1) {
+                        const u32 tot = atomicAdd(&O.total, 0u);
+                        st_relaxed(P.status + tile, (tile == 0 ? kFlagPrefix : kFlagAgg) | (u64)tot);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.ofull[osl]));
+        }
+    }
+}
+
+}  // namespace dgx
