@@ -1,0 +1,76 @@
+//go:build dgx
+
+// Package codec -- cgo shim for codec.Decode (codec/codec.go:444) over libdgx.
+// NOT COMPILED IN THIS REPOSITORY (no Go toolchain in the build image); see
+// go/algo_dgx.go and INTEGRATION.md.
+package codec
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../include
+#cgo LDFLAGS: -ldgx
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "dgx.h"
+*/
+import "C"
+
+import (
+	"unsafe"
+
+	"github.com/dgraph-io/dgraph/v25/protos/pb"
+)
+
+const dgxMinDecode = 1 << 16
+
+// flatten copies pb.UidPack (Blocks []*UidBlock: pointers to structs, each with its
+// own Deltas slice) into the struct-of-arrays dgx_pack_view, in C memory: cgo cannot
+// pass Go memory that contains Go pointers.
+func flatten(pack *pb.UidPack) (C.dgx_pack_view, func()) {
+	nb := len(pack.Blocks)
+	total := 0
+	for _, b := range pack.Blocks {
+		total += len(b.Deltas)
+	}
+	base := (*[1 << 28]C.uint64_t)(C.malloc(C.size_t(nb*8 + 8)))
+	num := (*[1 << 28]C.uint32_t)(C.malloc(C.size_t(nb*4 + 4)))
+	off := (*[1 << 28]C.uint64_t)(C.malloc(C.size_t(nb*8 + 8)))
+	del := C.malloc(C.size_t(total + 16))
+	o := 0
+	for i, b := range pack.Blocks {
+		base[i] = C.uint64_t(b.Base)
+		num[i] = C.uint32_t(b.NumUids)
+		off[i] = C.uint64_t(o)
+		if len(b.Deltas) > 0 {
+			C.memcpy(unsafe.Add(del, o), unsafe.Pointer(&b.Deltas[0]), C.size_t(len(b.Deltas)))
+		}
+		o += len(b.Deltas)
+	}
+	off[nb] = C.uint64_t(o)
+	var v C.dgx_pack_view
+	v.block_size = C.uint32_t(pack.BlockSize)
+	v.nblocks = C.size_t(nb)
+	v.base = (*C.uint64_t)(unsafe.Pointer(base))
+	v.num_uids = (*C.uint32_t)(unsafe.Pointer(num))
+	v.delta_off = (*C.uint64_t)(unsafe.Pointer(off))
+	v.deltas = (*C.uint8_t)(del)
+	return v, func() { C.free(unsafe.Pointer(base)); C.free(unsafe.Pointer(num)); C.free(unsafe.Pointer(off)); C.free(del) }
+}
+
+// Decode keeps codec/codec.go:444's contract: uids from Seek(seek, SeekStart) onward,
+// a non-nil (possibly empty) slice, sized with ExactLen (ApproxLen is 0 for
+// BlockSize-0 packs and only an estimate otherwise).
+func Decode(pack *pb.UidPack, seek uint64) []uint64 {
+	n := ExactLen(pack)
+	if pack == nil || n < dgxMinDecode {
+		return decodeGo(pack, seek)
+	}
+	view, free := flatten(pack)
+	defer free()
+	out := make([]uint64, n)
+	var outLen C.size_t
+	if rc := C.dgx_decode(&view, C.uint64_t(seek), (*C.uint64_t)(unsafe.Pointer(&out[0])), C.size_t(n), &outLen); rc != C.DGX_OK {
+		return decodeGo(pack, seek)
+	}
+	return out[:int(outLen)]
+}

@@ -1,0 +1,30 @@
+"""Builds and runs the C++ host mirror's known-answer tests (include/dgx_algo.hpp over the
+C ABI), which transcribe the Go tests of algo/uidlist_test.go."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build(tmp):
+    exe = os.path.join(tmp, "test_algo_kat")
+    subprocess.check_call([
+        "g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+        os.path.join(ROOT, "tests", "cpp", "test_algo_kat.cpp"), "-o", exe,
+        "-L", os.path.join(ROOT, "dgraph_b200"), "-ldgx", "-Wl,-rpath," + os.path.join(ROOT, "dgraph_b200"),
+    ])
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    build(str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_known_answers(tmp_path):
+    exe = build(str(tmp_path))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
