@@ -137,7 +137,8 @@ constexpr u64 kValMask = (1ull << 62) - 1;
 // nearest inclusive prefix and publishes this tile's inclusive prefix.
 // Returns the exclusive prefix of the tile (same value in every lane).
 // kPublished: the tile's aggregate word has already been stored by someone else.
-template <bool kPublished = false>
+// kBackoff: sleep between polls (the caller is a helper warp that must not steal issue slots).
+template <bool kPublished = false, bool kBackoff = false>
 __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 aggregate, int lane) {
     if (tile == 0) {
         if (lane == 0) st_relaxed(status, kFlagPrefix | aggregate);
@@ -150,7 +151,7 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 agg
         long long my = idx - lane;
         u64 w;
         if (my >= 0) {
-            do { w = ld_relaxed(status + my); } while ((w >> 62) == 0);
+            while (((w = ld_relaxed(status + my)) >> 62) == 0) { if (kBackoff) __nanosleep(100); }
         } else {
             w = kFlagPrefix;  // virtual tile before the first: prefix 0
         }

@@ -116,6 +116,22 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Same wait for the pipeline's helper warps: the try_wait carries a suspend-time hint and a miss
+// backs off with nanosleep, so a waiting warp does not compete with working warps for issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(u32 bar, u32 parity) {
+    u32 done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
+}
+
 struct __align__(128) DWarpSmem {
     unsigned char payload[D_WB + 64];
     unsigned short goff[D_MAXG * D_TSTRIDE + 2];

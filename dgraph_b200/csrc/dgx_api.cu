@@ -22,6 +22,7 @@
 #include "filter_kernel.cuh"
 #include "filter_pipe.cuh"
 #include "merge_kernel.cuh"
+#include "merge_multi.cuh"
 
 using namespace dgx;
 
@@ -64,6 +65,8 @@ static u32 g_stream_ratio = 16;
 static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's slice staging capacity
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
+static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
+static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
 static int g_num_sms = 148;
 constexpr size_t kPipeSmemMax = 220 * 1024;
@@ -185,8 +188,11 @@ extern "C" int dgx_init(int device) {
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * F_TA * sizeof(u64) + kScapMax)));
     CK(cudaFuncSetAttribute(filter_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
+    CK(cudaFuncSetAttribute(mmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * MM_C * sizeof(u64))));
     g_num_sms = prop.multiProcessorCount;
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
+    if (const char* s = getenv("DGX_MERGE")) g_merge_multi = (strcmp(s, "tree") != 0);
+    if (const char* s = getenv("DGX_MERGE_MULTI_MIN")) g_merge_multi_min = (size_t)atoll(s);
     if (const char* s = getenv("DGX_PIPE_MIN_K")) g_pipe_min_k = (size_t)std::max(1, atoi(s));
     if (const char* s = getenv("DGX_SCAP")) {
         int v = atoi(s);
@@ -465,6 +471,11 @@ extern "C" int dgx_dev_filter_batch(dgx_lane* l, int op, const uint64_t* const* 
 // ---------------------------------------------------------------------------
 // MergeSorted, device level: tree of batched 2-way unions
 // ---------------------------------------------------------------------------
+static int merge_tree_impl(dgx_lane* l, std::vector<MRef> cur, std::vector<uint64_t> ub, uint64_t total,
+                           uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
+static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const std::vector<uint64_t>& ub, uint64_t total,
+                            uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
+
 static int merge_sorted_impl(dgx_lane* l, const ListDesc* lists, size_t k, uint64_t* d_out, size_t out_cap,
                              uint64_t* d_out_len) {
     // nil / empty lists are skipped (algo/uidlist.go:400-403)
@@ -483,6 +494,14 @@ static int merge_sorted_impl(dgx_lane* l, const ListDesc* lists, size_t k, uint6
         return DGX_OK;
     }
     if (out_cap < total) return fail(DGX_ERR_CAP, "MergeSorted needs out_cap >= sum(lens) = %llu", (unsigned long long)total);
+    if (g_merge_multi && cur.size() >= 3 && cur.size() <= (size_t)MM_K && total >= g_merge_multi_min)
+        return merge_multi_impl(l, cur, ub, total, d_out, out_cap, d_out_len);
+    return merge_tree_impl(l, cur, ub, total, d_out, out_cap, d_out_len);
+}
+
+// Pairwise merge tree: ceil(log2 k) passes of merge_kernel.
+static int merge_tree_impl(dgx_lane* l, std::vector<MRef> cur, std::vector<uint64_t> ub, uint64_t total,
+                           uint64_t* d_out, size_t out_cap, uint64_t* d_out_len) {
     // number of levels; a single list still takes one pass (in-list de-duplication)
     int levels = 0;
     for (size_t n = cur.size(); n > 1; n = (n + 1) / 2) ++levels;
@@ -573,6 +592,91 @@ static int merge_sorted_impl(dgx_lane* l, const ListDesc* lists, size_t k, uint6
         spos += L.ntiles + 2;
     }
     CK(cudaMemcpyAsync(d_out_len, d_off + plan[levels - 1].off_index + 1, sizeof(u64), cudaMemcpyDeviceToDevice, l->stream));
+    return DGX_OK;
+}
+
+// Single-pass multiway merge (merge_multi.cuh) for 3..64 runs.
+static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const std::vector<uint64_t>& ub, uint64_t total,
+                            uint64_t* d_out, size_t out_cap, uint64_t* d_out_len) {
+    const size_t k = runs.size();
+    // Samples per run proportional to its length.  Every 4th distinct sample becomes a splitter, so a
+    // tile is the sum of 4 sample gaps (~2K values on average, Gamma-distributed instead of
+    // exponential) and rarely overflows the 4096-value shared-memory chunk.
+    const u32 stride = 4;
+    const uint64_t ntarget = std::min<uint64_t>(std::max<uint64_t>(total / 512, 1), uint64_t(1) << 24);
+    std::vector<u32> soff(k + 1, 0);
+    for (size_t j = 0; j < k; ++j) soff[j + 1] = soff[j] + (u32)((unsigned __int128)ub[j] * ntarget / total);
+    const u32 nsamp = soff[k];
+    void *h_raw, *d_raw;
+    const size_t runs_b = k * sizeof(MRef), soff_b = (k + 1) * sizeof(u32);
+    int rc = l->host.alloc(runs_b + soff_b, &h_raw);
+    if (rc) return rc;
+    memcpy(h_raw, runs.data(), runs_b);
+    memcpy((char*)h_raw + runs_b, soff.data(), soff_b);
+    const size_t a_samples = ((runs_b + soff_b + 255) & ~size_t(255));
+    const size_t a_split = a_samples + (size_t)(nsamp + 1) * 8;
+    const size_t a_nsplit = a_split + (size_t)(nsamp + 1) * 8;
+    const size_t a_bounds = a_nsplit + 256;
+    const size_t a_tin = a_bounds + (size_t)(nsamp + 2) * k * 8;
+    const size_t a_tout = a_tin + (size_t)(nsamp + 2) * 8;
+    const size_t a_tcnt = a_tout + (size_t)(nsamp + 3) * 8;
+    const size_t a_end = a_tcnt + (size_t)(nsamp + 2) * 4;
+    rc = l->ws.alloc(a_end, &d_raw);
+    if (rc) return rc;
+    void* d_scratch;
+    rc = l->ws.alloc(total * sizeof(u64), &d_scratch);
+    if (rc) return rc;
+    char* d = (char*)d_raw;
+    CK(cudaMemcpyAsync(d, h_raw, runs_b + soff_b, cudaMemcpyHostToDevice, l->stream));
+    MMParams P;
+    P.runs = (const MRef*)d;
+    P.k = (u32)k;
+    P.samp_off = (const u32*)(d + runs_b);
+    P.nsamp = nsamp;
+    P.stride = stride;
+    P.samples = (u64*)(d + a_samples);
+    P.splitters = (u64*)(d + a_split);
+    P.nsplit = (const u64*)(d + a_nsplit);
+    P.bounds = (u64*)(d + a_bounds);
+    P.tile_in = (u64*)(d + a_tin);
+    P.tile_out = (u64*)(d + a_tout);
+    P.tile_cnt = (u32*)(d + a_tcnt);
+    P.scratch = (u64*)d_scratch;
+    P.out = (u64*)d_out;
+    P.out_cap = out_cap;
+    P.out_len = (u64*)d_out_len;
+    P.err = l->d_err;
+    if (nsamp) {
+        msample_kernel<<<(nsamp + 255) / 256, 256, 0, l->stream>>>(P);
+        CK(cudaGetLastError());
+        l->launches += 1;
+        g_stats.launches += 1;
+        // the sample runs are sorted: the merge tree (with de-duplication) yields the distinct splitters
+        std::vector<MRef> sruns;
+        std::vector<uint64_t> sub;
+        for (size_t j = 0; j < k; ++j) {
+            const u32 sj = soff[j + 1] - soff[j];
+            if (!sj) continue;
+            sruns.push_back(MRef{P.samples + soff[j], nullptr, (u64)sj});
+            sub.push_back(sj);
+        }
+        rc = merge_tree_impl(l, sruns, sub, nsamp, (uint64_t*)P.splitters, nsamp, (uint64_t*)(d + a_nsplit));
+        if (rc) return rc;
+    } else {
+        CK(cudaMemsetAsync(d + a_nsplit, 0, 8, l->stream));
+    }
+    const u32 max_tiles = nsamp / stride + 1;
+    const uint64_t nb = (uint64_t)(max_tiles + 1) * k;
+    mplan_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
+    CK(cudaGetLastError());
+    mmerge_kernel<<<max_tiles, MM_NT, 2 * MM_C * sizeof(u64), l->stream>>>(P);
+    CK(cudaGetLastError());
+    mscan_kernel<<<1, 1024, 0, l->stream>>>(P);
+    CK(cudaGetLastError());
+    mcompact_kernel<<<max_tiles, 256, 0, l->stream>>>(P);
+    CK(cudaGetLastError());
+    l->launches += 4;
+    g_stats.launches += 4;
     return DGX_OK;
 }
 

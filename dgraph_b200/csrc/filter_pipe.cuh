@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             const u32 slot = seq % P_RING, use = seq / P_RING;
             const u32 base_ticket = __shfl_sync(0xffffffffu, next_base, 0);
             if (lane == 0) next_base = atomicAdd(P.ticket, 2u);  // prefetch (harmless past the end)
-            if (u == 0) mbar_wait(smem_u32(&S.freed[slot]), (use & 1u) ^ 1u);
+            if (u == 0) mbar_wait_relaxed(smem_u32(&S.freed[slot]), (use & 1u) ^ 1u);
             __syncwarp();
             const u64 tile64 = (u64)base_ticket + h;
             const bool valid = tile64 < (u64)P.ntiles;
@@ -318,10 +318,10 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
         // =========================== T: TMA warp ====================================
         for (u32 seq = 0;; ++seq) {
             const u32 slot = seq % P_RING, use = seq / P_RING;
-            mbar_wait(smem_u32(&S.ready[slot]), use & 1u);
+            mbar_wait_relaxed(smem_u32(&S.ready[slot]), use & 1u);
             const PDesc& D = S.ring[slot];
             const u32 st = seq & 1u, suse = seq >> 1;
-            mbar_wait(smem_u32(&S.empty[st]), (suse & 1u) ^ 1u);
+            mbar_wait_relaxed(smem_u32(&S.empty[st]), (suse & 1u) ^ 1u);
             PStageInfo& G = S.st[st];
             const u32 tile = D.tile;
             if (tile == P_END) {
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
         // =========================== O: output warp =================================
         for (u32 it = 0;; ++it) {
             const u32 sl = it % P_OS, use = it / P_OS;
-            mbar_wait(smem_u32(&S.ofull[sl]), use & 1u);
+            mbar_wait_relaxed(smem_u32(&S.ofull[sl]), use & 1u);
             const POutSlot& O = S.os[sl];
             const u32 tile = O.tile;
             if (tile == P_END) break;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 if (lane >= dlt) incl += v;
             }
             const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-            const u64 base = lookback_exclusive<true>(P.status, tile, (u64)total, lane);
+            const u64 base = lookback_exclusive<true, true>(P.status, tile, (u64)total, lane);
             if (lane == 0) {
                 if ((u64)tile == P.tasks[q].tile_base) P.out_off[q] = base;
                 if (tile == P.ntiles - 1) P.out_off[P.ntasks] = base + (u64)total;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             if (lane == 0) mbar_arrive(smem_u32(&S.empty[st]));
 
             // ---- survivors -> this warp's segment of the output slot -----------------------------
-            mbar_wait(smem_u32(&S.oempty[osl]), (ouse & 1u) ^ 1u);
+            mbar_wait_relaxed(smem_u32(&S.oempty[osl]), (ouse & 1u) ^ 1u);
             {
                 u64* od = s_out + (size_t)osl * P_TA + P_WC * wid;
                 const unsigned lt = (1u << lane) - 1u;

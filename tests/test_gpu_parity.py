@@ -353,3 +353,46 @@ def test_properties_at_scale(dgx):
     eq(m.Uids, a, "merge(A∩B, A\\B) == A")
     m2 = dgx.algo.MergeSorted([la, lb, la])
     eq(m2.Uids, np.union1d(a, b), "union")
+
+
+def test_merge_multiway_forced(orc):
+    """The multiway MergeSorted path with its size threshold removed (DGX_MERGE_MULTI_MIN=0), in a
+    subprocess because libdgx reads its knobs once: known answers, random k, adversarial shapes that
+    force the block-wise rounds (identical lists, one dense cluster, long duplicate runs)."""
+    import subprocess
+    code = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import gen
+from dgraph_b200 import algo, pb
+from oracle import pyoracle as orc
+from test_oracle_algo import MERGE_CASES
+def L(x): return pb.List(np.asarray(x, dtype=np.uint64))
+def chk(lists, what):
+    got = algo.MergeSorted([L(l) for l in lists]).Uids
+    want = orc.merge_sorted(lists)
+    assert got.size == want.size and np.array_equal(got, want), (what, got.size, want.size)
+for lists, want in MERGE_CASES:
+    got = algo.MergeSorted([L(l) for l in lists])
+    assert got.tolist() == want, (lists, got.tolist())
+rng = np.random.default_rng(77)
+for k in (3, 4, 5, 17, 33, 63, 64):
+    chk([np.sort(rng.integers(0, 50000, int(rng.integers(0, 3000)), dtype=np.uint64)) for _ in range(k)], f"small k={k}")
+master = gen.zipf_gaps(rng, 400000)
+chk([master] * 64, "64 identical lists")
+chk([master[::3], master[1::3], master[2::3]] * 8, "interleaved x8")
+dense = np.arange(10**6, 10**6 + 300000, dtype=np.uint64)
+chk([dense] + [gen.thin(rng, master, 0.01) for _ in range(40)], "one dense cluster")
+runs = np.sort(np.concatenate([np.full(50000, 7), np.full(70000, 9), rng.integers(0, 100, 5000)]).astype(np.uint64))
+chk([runs, runs[::2], np.arange(0, 200, dtype=np.uint64)] * 5, "long duplicate runs")
+lens = (2_000_000 / np.arange(1, 65)).astype(int)
+big = gen.zipf_gaps(rng, 4_000_000)
+chk([gen.thin(rng, big, min(1.0, l / big.size)) for l in lens], "config-5 shape")
+chk([np.array([2**64 - 1, 2**64 - 1], dtype=np.uint64), np.array([0, 2**64 - 1], dtype=np.uint64), np.array([5], dtype=np.uint64)], "max values")
+print("MULTIWAY_OK")
+'''
+    env = dict(os.environ, DGX_MERGE_MULTI_MIN="0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert "MULTIWAY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
