@@ -23,7 +23,7 @@ namespace dgx {
 constexpr int D_WARPS = 4;                  // warps per CTA
 constexpr int D_NT = D_WARPS * 32;
 constexpr int D_BPW = 64;                   // blocks owned by one warp
-constexpr int D_WB = 8192;                  // payload window per warp (bytes)
+constexpr int D_WB = 4096;                  // payload window per warp (bytes)
 constexpr int D_MAXG = 64;                  // groups per block at BlockSize 256
 constexpr int D_TSTRIDE = 33;               // group-offset table row stride (u16)
 constexpr int D_STAGE = 260;                // staging row (u64)
