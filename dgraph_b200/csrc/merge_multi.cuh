@@ -28,7 +28,7 @@
 namespace dgx {
 
 constexpr int MM_K = 64;          // maximum fan-in
-constexpr int MM_NT = 256;        // threads per merge CTA
+constexpr int MM_NT = 512;        // threads per merge CTA
 constexpr int MM_C = 4096;        // values merged in shared memory at once
 constexpr int MM_VT = MM_C / MM_NT;
 
@@ -123,7 +123,7 @@ __device__ __forceinline__ void mm_merge_level(const u64* src, u64* dst, const i
     }
 }
 
-__global__ void __launch_bounds__(MM_NT) mmerge_kernel(const MMParams P) {
+__global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
     extern __shared__ __align__(16) u64 s_mm[];  // two ping-pong buffers of MM_C values
     u64* s_x = s_mm;
     u64* s_y = s_mm + MM_C;
