@@ -36,6 +36,53 @@ def lpt_partition(costs: Sequence[int], world: int) -> List[np.ndarray]:
     return [np.nonzero(owner == r)[0] for r in range(world)]
 
 
+def contiguous_partition(costs: Sequence[int], world: int) -> List[np.ndarray]:
+    """Split units 0..n-1 into `world` CONTIGUOUS blocks of roughly equal cost (cut at the cost
+    prefix nearest to r/world of the total).  Imbalance is at most one unit's cost; in exchange a
+    rank's results are already contiguous in unit order, so the final concatenation needs no
+    scatter: rank payloads are simply laid end to end."""
+    costs = np.asarray(costs, dtype=np.int64)
+    n = costs.size
+    pref = np.concatenate([[0], np.cumsum(costs)])
+    total = int(pref[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r // world
+        c = int(np.searchsorted(pref, target, side="left"))
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return [np.arange(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def gatherv_contiguous(dist, local_out, local_off, device=None):
+    """All-gatherv for contiguous shards (contiguous_partition): returns (out, off) in unit order.
+    local_off: this rank's CSR offsets (len = units + 1).  Counts travel first, then payloads padded
+    to the largest shard; rank payloads are laid end to end."""
+    import torch
+
+    world = dist.get_world_size()
+    dev = local_out.device if device is None else device
+    meta = torch.tensor([local_off.numel() - 1, int(local_off[-1].item())], dtype=torch.int64, device=dev)
+    metas = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    nun = [int(m[0].item()) for m in metas]
+    tot = [int(m[1].item()) for m in metas]
+    max_u, max_t = max(max(nun), 1), max(max(tot), 1)
+    lens_local = torch.zeros(max_u, dtype=torch.int64, device=dev)
+    lens_local[: local_off.numel() - 1] = local_off[1:] - local_off[:-1]
+    lens_all = torch.empty(world * max_u, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens_all, lens_local)
+    pay_local = torch.empty(max_t, dtype=torch.int64, device=dev)
+    pay_local[: int(local_off[-1].item())] = local_out[: int(local_off[-1].item())]
+    pay_all = torch.empty(world * max_t, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(pay_all, pay_local)
+    lens_g = torch.cat([lens_all[r * max_u: r * max_u + nun[r]] for r in range(world)])
+    off_g = torch.zeros(lens_g.numel() + 1, dtype=torch.int64, device=dev)
+    off_g[1:] = torch.cumsum(lens_g, 0)
+    out_g = torch.cat([pay_all[r * max_t: r * max_t + tot[r]] for r in range(world)])
+    return out_g, off_g
+
+
 def shard_offsets(counts: np.ndarray) -> np.ndarray:
     out = np.zeros(counts.size + 1, dtype=np.int64)
     np.cumsum(counts, out=out[1:])

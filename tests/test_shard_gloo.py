@@ -84,3 +84,52 @@ def test_sharded_pairs_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_contiguous_partition():
+    from dgraph_b200.shard import contiguous_partition
+
+    rng = np.random.default_rng(1)
+    costs = rng.integers(1, 10**6, 997)
+    for world in (1, 2, 3, 8):
+        parts = contiguous_partition(costs, world)
+        assert np.array_equal(np.concatenate(parts), np.arange(997))
+        loads = np.array([costs[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= 2 * costs.max()
+    assert [p.tolist() for p in contiguous_partition([], 3)] == [[], [], []]
+    assert [p.tolist() for p in contiguous_partition([5], 3)][-1] == [0] or sum(len(p) for p in contiguous_partition([5], 3)) == 1
+
+
+def _worker_contig(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dgraph_b200.shard import contiguous_partition, gatherv_contiguous
+
+        rng = np.random.default_rng(7)
+        n = 23
+        results = [np.sort(rng.integers(0, 1000, int(rng.integers(0, 50)), dtype=np.int64)) for _ in range(n)]
+        parts = contiguous_partition([r.size + 1 for r in results], world)
+        mine = parts[rank]
+        outs = [results[u] for u in mine]
+        off = np.zeros(len(mine) + 1, dtype=np.int64)
+        if outs:
+            off[1:] = np.cumsum([o.size for o in outs])
+        cat = np.concatenate(outs + [np.zeros(0, np.int64)])
+        out, goff = gatherv_contiguous(dist, torch.from_numpy(cat.copy()), torch.from_numpy(off))
+        out, goff = out.numpy(), goff.numpy()
+        ok = goff.size == n + 1 and all(np.array_equal(out[goff[i]: goff[i + 1]], results[i]) for i in range(n))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gatherv_contiguous_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_contig, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -2,7 +2,7 @@
 """Multi-GPU runs of BASELINE configs C4 and C5 (one process per GPU, launched by torchrun):
 
   C4  batched independent 2-way intersections, sizes ~ power law on [1e4, 1e6]: units are
-      independent, so they are LPT-partitioned by bytes over the ranks (dgraph_b200/shard.py),
+      independent, so they are partitioned by bytes over the ranks (dgraph_b200/shard.py),
       every rank runs ONE batched libdgx launch on its units, and the results return in pair
       order through an NCCL all-gatherv.  No collective on the data path.
   C5  one huge MergeSorted (k = 64, total --merge-total UIDs) + Difference: the UID space is
@@ -54,7 +54,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.pop("NCCL_DEBUG", None)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -87,7 +87,7 @@ def main():
     rng = np.random.default_rng(401)
     u = rng.random(npairs)
     sizes = np.minimum((1e4 / (1 - u * (1 - 1e4 / 1e6))).astype(np.int64), 1_000_000)  # power law, alpha = 2
-    parts = shard.lpt_partition([16 * int(s) for s in sizes], world)
+    parts = shard.contiguous_partition([16 * int(s) for s in sizes], world)  # contiguous: no scatter on the way back
     mine = parts[rank]
     gen = torch.Generator(device=dev)
     lists, koff = [], [0]
@@ -112,7 +112,7 @@ def main():
     def c4_step():
         c4_compute()
         if world > 1:
-            res["g"] = shard.gatherv_results(dist, mine, out, off, npairs, device=dev)
+            res["g"] = shard.gatherv_contiguous(dist, out, off, device=dev)
         else:
             res["g"] = (out, off)
 
@@ -136,7 +136,7 @@ def main():
                           "ms": ms, "uids_per_s": int(tot.item()) / (ms * 1e-3),
                           "ms_compute_only": ms_compute, "uids_per_s_compute_only": int(tot.item()) / (ms_compute * 1e-3),
                           "out_uids": int(goff[-1].item()), "check": ok,
-                          "note": "LPT shard by bytes, one batched launch per rank, NCCL all-gatherv of results inside the timed region"}),
+                          "note": "contiguous shards balanced by bytes, one batched launch per rank, NCCL all-gatherv of results inside the timed region"}),
               flush=True)
     del lists, out
 
@@ -183,7 +183,7 @@ def main():
         _lib.check(lib.dgx_dev_filter_batch(lane, _lib.OP_DIFFERENCE, p2, l2, k2, 1, C.c_void_p(dout.data_ptr()),
                                             tot_local, C.c_void_p(doff.data_ptr())))
         if world > 1 and gather:
-            res5["g"] = shard.gatherv_results(dist, np.array([rank]), dout, doff, world, device=dev)
+            res5["g"] = shard.gatherv_contiguous(dist, dout, doff, device=dev)
         else:
             res5["g"] = (dout, doff)
 
