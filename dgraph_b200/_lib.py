@@ -57,6 +57,7 @@ SYMBOLS = {
     "dgx_intersect_batch": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz]),
     "dgx_decode": (_int, [C.POINTER(PackView), _u64, _vp, _sz, _szp]),
     "dgx_decode_intersect_sorted": (_int, [C.POINTER(PackView), _u64, _vp, _vp, _sz, _vp, _sz, _szp]),
+    "dgx_intersect_compressed": (_int, [C.POINTER(PackView), _u64, _vp, _sz, _vp, _sz, _szp]),
     "dgx_lane_create": (_vp, [_int, _vp]),
     "dgx_lane_destroy": (None, [_vp]),
     "dgx_lane_sync": (_int, [_vp]),

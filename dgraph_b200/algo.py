@@ -85,6 +85,24 @@ def Difference(u: List, v: List) -> List:
     return List(out[: n.value])
 
 
+def IntersectCompressedWith(pack, afterUID: int, v: List, o: List) -> None:
+    """algo.IntersectCompressedWith(pack, afterUID, v, o) (algo/uidlist.go:33-61): o.Uids = v ∩ pack[>= afterUID].
+
+    A nil pack leaves `o` untouched, like the reference (:34-36)."""
+    if pack is None:
+        return
+    from .codec import view_of
+
+    lib = _lib.load()
+    vv = np.zeros(0, np.uint64) if v.Uids is None else v.Uids
+    out = np.empty(max(vv.size, 1), dtype=np.uint64)
+    n = C.c_size_t(0)
+    pack = pack.normalized()
+    view = view_of(pack)
+    _lib.check(lib.dgx_intersect_compressed(C.byref(view), afterUID, _p(vv), vv.size, _p(out), vv.size, C.byref(n)))
+    o.Uids = out[: n.value]
+
+
 def IntersectBatch(a: np.ndarray, a_off: np.ndarray, b: np.ndarray, b_off: np.ndarray):
     """Batched independent IntersectWith in CSR form (dgx_intersect_batch).
 

@@ -1053,3 +1053,14 @@ extern "C" int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek
     if (rc) return rc;
     return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, out, out_cap, out_len);
 }
+
+extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
+                                        uint64_t* out, size_t out_cap, size_t* out_len) {
+    if (p == nullptr) {  // `if pack == nil { return }` (algo/uidlist.go:34-36): o is left untouched -> length 0 here
+        if (out_len) *out_len = 0;
+        return DGX_OK;
+    }
+    const uint64_t* lists[1] = {v};
+    const size_t lens[1] = {m};
+    return dgx_decode_intersect_sorted(p, after_uid, lists, lens, 1, out, out_cap, out_len);
+}

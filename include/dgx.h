@@ -126,6 +126,16 @@ int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek,
                                 const uint64_t* const* lists, const size_t* lens, size_t k,
                                 uint64_t* out, size_t out_cap, size_t* out_len);
 
+/* algo.IntersectCompressedWith(pack *pb.UidPack, afterUID uint64, v, o *pb.List)
+ *                                                        algo/uidlist.go:33-61
+ * o.Uids = v ∩ (uids of pack from Decoder.Seek(afterUID, SeekStart) onward) -- the entry
+ * point posting.List.Uids uses for filtered reads (posting/list.go:1795-1800).  The pack
+ * crosses PCIe compressed and is decoded on the device; the reference's LinJump / Bin
+ * split (:49-59) only changes how the same set is computed.  out_cap >= m.
+ * Defined, like the reference's own tests, for duplicate-free inputs. */
+int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
+                             uint64_t* out, size_t out_cap, size_t* out_len);
+
 /* ---- device-resident API ------------------------------------------------- */
 /* For callers that keep posting lists in HBM (a pack / list cache) and for
  * roofline measurement.  All pointers named d_* are device pointers on the

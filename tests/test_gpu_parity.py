@@ -293,6 +293,32 @@ def test_decode_intersect_pipeline(dgx, orc):
         eq(got.Uids, want, f"pipeline seek={seek}")
 
 
+def test_intersect_compressed_with(dgx, orc):
+    """algo.IntersectCompressedWith vs the oracle's restatement (LinJump and Bin branches,
+    afterUID seeks), on duplicate-free inputs like the reference's own tests
+    (algo/uidlist_test.go:607-681)."""
+    rng = np.random.default_rng(21)
+    # the reference's fillNums cases at BlockSize 10
+    for n1 in (0, 1, 3, 11, 100):
+        for n2 in (0, 1, 3, 11, 100):
+            common, block, other = gen.fill_nums(rng, n1, n2)
+            pack = orc.encode(block, 10)
+            o = dgx.pb.List(None)
+            dgx.algo.IntersectCompressedWith(to_pack(dgx, pack), 0, L(dgx, other), o)
+            if pack.is_nil:
+                assert o.Uids is None
+            else:
+                eq(o.Uids, common, f"fillNums {n1},{n2}")
+    for n, m in ((1000, 1000), (1000, 50), (50, 20000), (5000, 30), (300000, 2000), (2000, 300000)):
+        u = gen.uniform_unique(rng, n, 10 * max(n, m))
+        v = gen.uniform_unique(rng, m, 10 * max(n, m))
+        pack = orc.encode(u, 256)
+        for after in (0, 1, int(u[n // 2]), int(u[n // 2]) + 1, int(u[-1]), int(u[-1]) + 5):
+            o = dgx.pb.List(None)
+            dgx.algo.IntersectCompressedWith(to_pack(dgx, pack), after, L(dgx, v), o)
+            eq(o.Uids, orc.intersect_compressed_with(pack, after, v), f"n={n} m={m} after={after}")
+
+
 # ---- error behaviour, concurrency, properties at size --------------------------------
 
 def test_out_cap_error(dgx):

@@ -273,6 +273,67 @@ def main():
                     ms + ms_i, tot, pack_bytes + 8 * n3 + 8 * (tot + ni), ok))
     L.lib.dgx_dev_pack_free(pk)
 
+    # ---- C3 end to end through the host-pointer C ABI: the pack crosses PCIe COMPRESSED ---------
+    # (dgx_decode_intersect_sorted: H2D of the pack + the two lists, decode and intersect on the
+    # device, D2H of the result) against the CPU oracle doing codec.Decode + algo.IntersectSorted.
+    h1 = l1.cpu().numpy().view(np.uint64)
+    h2 = l2.cpu().numpy().view(np.uint64)
+    hp = (C.c_void_p * 2)(h1.ctypes.data, h2.ctypes.data)
+    hl = (C.c_size_t * 2)(h1.size, h2.size)
+    hout = np.empty(h2.size, dtype=np.uint64)
+    hn = C.c_size_t(0)
+
+    def e2e():
+        _lib.check(L.lib.dgx_decode_intersect_sorted(C.byref(view), 0, hp, hl, 2, hout.ctypes.data_as(C.c_void_p),
+                                                      hout.size, C.byref(hn)))
+
+    e2e()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e()
+    t_e2e = (time.perf_counter() - t0) / 3
+    ok = bool(hn.value == ni and np.array_equal(hout[: hn.value], iout[:ni].cpu().numpy().view(np.uint64)))
+    t1 = time.perf_counter()
+    dec_cpu = orc.decode(spack, 0)          # the 2e7-UID sample pack, scaled below
+    t_dec = (time.perf_counter() - t1) * (n3 / sample.size)
+    t1 = time.perf_counter()
+    orc.intersect_sorted([host, h1, h2])
+    t_int = time.perf_counter() - t1
+    r = row("Decode + IntersectSorted (host pointers, e2e)",
+            "C3 through dgx_decode_intersect_sorted: pack (compressed) and lists cross PCIe, result comes back",
+            t_e2e * 1e3, tot, pack_bytes + 8 * (l1.numel() + l2.numel()) + 8 * ni, ok,
+            {"h2d_bytes": pack_bytes + 8 * (h1.size + h2.size), "cpu_oracle_ms": (t_dec + t_int) * 1e3,
+             "cpu_oracle_decode_ms": t_dec * 1e3, "cpu_oracle_intersect_ms": t_int * 1e3,
+             "speedup_vs_cpu_1thread": (t_dec + t_int) / t_e2e,
+             "note": "algorithmic bytes here = bytes that cross PCIe; the CPU figure is the single-threaded oracle (decode scaled from a 2e7-UID sample)"})
+    rows.append(r)
+    # same call with every input in pinned host memory (dgx_host_alloc): PCIe at DMA speed
+    def pin(a):
+        ptr = L.lib.dgx_host_alloc(max(a.nbytes, 16))
+        C.memmove(ptr, a.ctypes.data, a.nbytes)
+        return ptr
+    pview = _lib.PackView()
+    pview.block_size, pview.nblocks = 256, pack.nblocks
+    pins = [pin(base), pin(num), pin(doff_), pin(deltas), pin(h1), pin(h2)]
+    pview.base, pview.num_uids, pview.delta_off, pview.deltas = pins[0], pins[1], pins[2], pins[3]
+    php = (C.c_void_p * 2)(pins[4], pins[5])
+
+    def e2e_pinned():
+        _lib.check(L.lib.dgx_decode_intersect_sorted(C.byref(pview), 0, php, hl, 2, hout.ctypes.data_as(C.c_void_p),
+                                                      hout.size, C.byref(hn)))
+
+    e2e_pinned()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e_pinned()
+    t_pin = (time.perf_counter() - t0) / 3
+    ok = bool(hn.value == ni and np.array_equal(hout[: hn.value], iout[:ni].cpu().numpy().view(np.uint64)))
+    rows.append(row("Decode + IntersectSorted (pinned host pointers, e2e)", "as above, inputs in dgx_host_alloc memory",
+                    t_pin * 1e3, tot, pack_bytes + 8 * (l1.numel() + l2.numel()) + 8 * ni, ok,
+                    {"speedup_vs_cpu_1thread": (t_dec + t_int) / t_pin, "cpu_oracle_ms": (t_dec + t_int) * 1e3}))
+    for ptr in pins:
+        L.lib.dgx_host_free(ptr)
+
     if args.out:
         with open(args.out, "w") as f:
             json.dump(rows, f, indent=1)
