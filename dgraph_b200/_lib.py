@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdgx.so")
+SO_PATH = os.environ.get("DGX_LIB") or os.path.join(_HERE, "libdgx.so")  # DGX_LIB: try an experimental build
 
 DGX_OK = 0
 STATUS_NAMES = {0: "DGX_OK", -1: "DGX_ERR_CUDA", -2: "DGX_ERR_OOM", -3: "DGX_ERR_ARG", -4: "DGX_ERR_CAP", -5: "DGX_ERR_NODEV"}

@@ -439,7 +439,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         cap = std::min<size_t>(std::max<size_t>(cap, P_TA + P_TA / 8), 9216) & ~size_t(1);
         PP.slice_cap = (u32)cap;
         const size_t smem = ((sizeof(PShared) + 127) & ~size_t(127)) + (1 + P_OS) * P_TA * sizeof(u64) +
-                            2 * ((P_TA + 2) + cap) * sizeof(u64);
+                            P_ST * ((P_TA + 2) + cap) * sizeof(u64);
         if (smem > kPipeSmemMax) return fail(DGX_ERR_ARG, "pipeline stage too large");
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pipe_kernel, P_NT, smem));

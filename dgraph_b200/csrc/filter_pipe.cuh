@@ -34,13 +34,20 @@
 
 namespace dgx {
 
-constexpr int P_CW = 8;                  // consumer warps
+#ifndef DGX_P_CW
+#define DGX_P_CW 8
+#endif
+constexpr int P_CW = DGX_P_CW;           // consumer warps
 constexpr int P_CT = P_CW * 32;          // consumer threads
 constexpr int P_NT = P_CT + 96;          // + metadata warp + TMA warp + output warp
 constexpr int P_VA = 2;                  // candidate rows per consumer warp
 constexpr int P_WC = 32 * P_VA;          // candidates per consumer warp
 constexpr int P_TA = P_CW * 64;          // candidates per tile
 constexpr int P_OS = 4;                  // output slots in flight
+#ifndef DGX_P_ST
+#define DGX_P_ST 2
+#endif
+constexpr int P_ST = DGX_P_ST;           // data stages in flight
 constexpr int P_MAXL = 8;                // filter lists a stage can hold
 constexpr int P_RING = 4;                // tile descriptors in flight between M and T
 constexpr u32 P_END = 0xffffffffu;
@@ -152,9 +159,9 @@ struct POutSlot {              // survivors of one tile: warp w owns data[P_WC*w
     u32 cnt[P_CW];
 };
 struct PShared {
-    u64 full[2], empty[2], ofull[P_OS], oempty[P_OS], ready[P_RING], freed[P_RING];
+    u64 full[P_ST], empty[P_ST], ofull[P_OS], oempty[P_OS], ready[P_RING], freed[P_RING];
     PDesc ring[P_RING];
-    PStageInfo st[2];
+    PStageInfo st[P_ST];
     POutSlot os[P_OS];
 };
 
@@ -255,11 +262,11 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
     u64* s_out = s_work + P_TA;  // P_OS slots of P_TA values
     u64* stage_mem = s_work + (1 + P_OS) * P_TA;
     const size_t stage_words = (size_t)(P_TA + 2) + scap;
-    u64* s_A[2] = {stage_mem, stage_mem + stage_words};
-    u64* s_SL[2] = {stage_mem + (P_TA + 2), stage_mem + stage_words + (P_TA + 2)};
+    auto s_A = [&](u32 st_) { return stage_mem + (size_t)st_ * stage_words; };
+    auto s_SL = [&](u32 st_) { return stage_mem + (size_t)st_ * stage_words + (P_TA + 2); };
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), P_CW); }
+        for (int s = 0; s < P_ST; ++s) { mbar_init(smem_u32(&S.full[s]), 1); mbar_init(smem_u32(&S.empty[s]), P_CW); }
         for (int s = 0; s < P_OS; ++s) { mbar_init(smem_u32(&S.ofull[s]), P_CW); mbar_init(smem_u32(&S.oempty[s]), 1); }
         for (int r = 0; r < P_RING; ++r) { mbar_init(smem_u32(&S.ready[r]), 1); mbar_init(smem_u32(&S.freed[r]), 1); }
         for (int s = 0; s < P_OS; ++s) { S.os[s].total = 0; S.os[s].arrived = 0; }
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             const u32 slot = seq % P_RING, use = seq / P_RING;
             mbar_wait_relaxed(smem_u32(&S.ready[slot]), use & 1u);
             const PDesc& D = S.ring[slot];
-            const u32 st = seq & 1u, suse = seq >> 1;
+            const u32 st = seq % P_ST, suse = seq / P_ST;
             mbar_wait_relaxed(smem_u32(&S.empty[st]), (suse & 1u) ^ 1u);
             PStageInfo& G = S.st[st];
             const u32 tile = D.tile;
@@ -373,10 +380,10 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             if (lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (tot) mbar_expect_tx(bar, tot); else mbar_arrive(bar);
-                if (bytesA) tma_bulk_g2s(smem_u32(s_A[st]), D.A + D.a0 - headA, bytesA, bar);
+                if (bytesA) tma_bulk_g2s(smem_u32(s_A(st)), D.A + D.a0 - headA, bytesA, bar);
             }
             __syncwarp();
-            if (my_bytes) tma_bulk_g2s(smem_u32(s_SL[st] + (incl - words)), src - head, my_bytes, bar);
+            if (my_bytes) tma_bulk_g2s(smem_u32(s_SL(st) + (incl - words)), src - head, my_bytes, bar);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.freed[slot]));  // descriptor consumed
         }
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
         // =========================== C: consumer warps ==============================
         u64* s_w = s_work + P_WC * wid;
         for (u32 it = 0;; ++it) {
-            const u32 st = it & 1u, suse = it >> 1;
+            const u32 st = it % P_ST, suse = it / P_ST;
             mbar_wait(smem_u32(&S.full[st]), suse & 1u);
             const PStageInfo& G = S.st[st];
             const u32 tile = G.tile;
@@ -438,8 +445,8 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 break;
             }
             const u32 na = G.na, k = G.k, q = G.task;
-            const u64* cand = s_A[st] + G.headA;
-            const u64* sl = s_SL[st];
+            const u64* cand = s_A(st) + G.headA;
+            const u64* sl = s_SL(st);
             PTile X;
             X.cand = cand; X.A = G.A; X.a0 = G.a0; X.prev = G.prev; X.has_prev = G.has_prev != 0;
             X.cidx0 = P_WC * wid + lane; X.op = P.op;
