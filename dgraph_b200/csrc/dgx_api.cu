@@ -433,6 +433,9 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         PP.plan_base = (const u64*)d_pb;
         PP.plan = (const PPlanEntry*)d_plan;
         PP.tiles = (const PTileEntry*)d_tiles;
+        // wide queries: one tile per ticket keeps the look-back order tight (measured 0.476 vs 0.50 ms on
+        // C2); 2-list batches have tiny tiles and amortise the metadata chain over two (measured +4 %)
+        PP.grp = kmax >= 4 ? 1u : 2u;
         const size_t nl = std::min<size_t>(std::max<size_t>(kmax - 1, 1), P_MAXL);
         size_t cap = (P_TA + P_TA / 8) * nl * (kmax <= 2 ? 4 : 1);
         if (g_scap_override) cap = g_scap_override / 8;

@@ -49,7 +49,8 @@ constexpr int P_OS = 4;                  // output slots in flight
 #endif
 constexpr int P_ST = DGX_P_ST;           // data stages in flight
 constexpr int P_MAXL = 8;                // filter lists a stage can hold
-constexpr int P_RING = 4;                // tile descriptors in flight between M and T
+constexpr int P_RING = 8;                // tile descriptors in flight between M and T
+constexpr int P_GRP = 4;                 // most tiles the metadata warp can resolve per iteration (8 lanes each)
 constexpr u32 P_END = 0xffffffffu;
 static_assert(P_CW * P_WC == P_TA, "tile geometry");
 
@@ -67,6 +68,7 @@ struct PParams {
     const struct PTileEntry* tiles;  // per tile
     u32 slice_cap;             // stage capacity for slices, in u64 values
     u32 nctas;
+    u32 grp;                   // tiles the metadata warp claims per ticket (1 .. P_GRP)
 };
 
 // ---- plan ---------------------------------------------------------------------------
@@ -277,23 +279,24 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
 
     if (wid == P_CW) {
         // =========================== M: metadata warp ===============================
-        // Two tiles per iteration (one per half-warp), claimed with ONE atomic so a CTA's
-        // tiles stay in look-back order; the ticket for the next iteration is fetched
-        // before this iteration's loads, so the chain per tile pair is two global
-        // latencies: tile table -> {list descriptors, plan entries}.  Sub-lane u < 8 of a
-        // half-warp resolves filter list u of its tile.
-        const int h = lane >> 4, u = lane & 15;
+        // Four tiles per iteration (eight lanes each), claimed with ONE atomic so a CTA's tiles
+        // stay in look-back order; the ticket for the next iteration is fetched before this
+        // iteration's loads, so the chain per group is two global latencies: tile table ->
+        // {list descriptors, plan entries}.  Sub-lane u < 8 resolves filter list u of its tile.
+        const int h = lane >> 3, u = lane & 7;
         u32 next_base = 0;
-        if (lane == 0) next_base = atomicAdd(P.ticket, 2u);
+        const u32 grp = PP.grp;
+        if (lane == 0) next_base = atomicAdd(P.ticket, grp);
         for (u32 itn = 0;; ++itn) {
-            const u32 seq = 2 * itn + h;
+            const u32 seq = grp * itn + h;
             const u32 slot = seq % P_RING, use = seq / P_RING;
             const u32 base_ticket = __shfl_sync(0xffffffffu, next_base, 0);
-            if (lane == 0) next_base = atomicAdd(P.ticket, 2u);  // prefetch (harmless past the end)
-            if (u == 0) mbar_wait_relaxed(smem_u32(&S.freed[slot]), (use & 1u) ^ 1u);
+            if (lane == 0) next_base = atomicAdd(P.ticket, grp);  // prefetch (harmless past the end)
+            const bool act = (u32)h < grp;  // lane groups beyond grp idle
+            if (act && u == 0) mbar_wait_relaxed(smem_u32(&S.freed[slot]), (use & 1u) ^ 1u);
             __syncwarp();
             const u64 tile64 = (u64)base_ticket + h;
-            const bool valid = tile64 < (u64)P.ntiles;
+            const bool valid = act && tile64 < (u64)P.ntiles;
             const u32 tile = valid ? (u32)tile64 : P_END;
             PTileEntry e;
             e.task = 0; e.list_first = 0; e.k = 0; e.na = 0; e.a0 = 0; e.plan_idx = 0; e.prev = 0; e.has_prev = 0;
@@ -312,14 +315,14 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 if (u == 0) A = P.lists[e.list_first].ptr;
             }
             PDesc& D = S.ring[slot];
-            if (u == 0) {
+            if (act && u == 0) {
                 D.tile = tile; D.task = e.task; D.na = e.na; D.k = e.k; D.list_first = e.list_first;
                 D.has_prev = e.has_prev; D.a0 = e.a0; D.prev = e.prev; D.plan_idx = e.plan_idx; D.A = A;
             }
-            if (u < P_MAXL) { D.ptr[u] = ptrj; D.len[u] = lenj; D.r0[u] = r0; D.r1[u] = r1; }
+            if (act && u < P_MAXL) { D.ptr[u] = ptrj; D.len[u] = lenj; D.r0[u] = r0; D.r1[u] = r1; }
             __syncwarp();
-            if (u == 0) mbar_arrive(smem_u32(&S.ready[slot]));
-            if (__ballot_sync(0xffffffffu, !valid)) break;  // an END descriptor was published
+            if (act && u == 0) mbar_arrive(smem_u32(&S.ready[slot]));
+            if (__ballot_sync(0xffffffffu, act && !valid)) break;  // an END descriptor was published
         }
     } else if (wid == P_CW + 1) {
         // =========================== T: TMA warp ====================================
