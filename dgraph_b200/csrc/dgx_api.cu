@@ -1067,3 +1067,16 @@ extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_u
     const size_t lens[1] = {m};
     return dgx_decode_intersect_sorted(p, after_uid, lists, lens, 1, out, out_cap, out_len);
 }
+
+#ifdef DGX_PIPE_PROF
+// Experimental builds only (not part of include/dgx.h): read and clear filter_pipe_kernel's wait counters.
+extern "C" int dgx_debug_pprof(uint64_t* out16) {
+    unsigned long long h[16];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(h, dgx::g_pprof, sizeof(h)));
+    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    memset(h, 0, sizeof(h));
+    CK(cudaMemcpyToSymbol(dgx::g_pprof, h, sizeof(h)));
+    return DGX_OK;
+}
+#endif

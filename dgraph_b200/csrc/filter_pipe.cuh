@@ -253,6 +253,20 @@ __device__ __forceinline__ bool phit(const PTile& X, u64 x, int i, unsigned dup,
     return (g < lenB) && (ld_probe(B + g) == x);
 }
 
+#ifdef DGX_PIPE_PROF
+// Wait-time breakdown per warp role (cycles, summed over warps / CTAs); experimental builds only.
+__device__ unsigned long long g_pprof[16];
+#define PPROF_VARS unsigned long long pp_t = 0, pp_w0 = 0, pp_w1 = 0, pp_w2 = 0; const long long pp_start = clock64();
+#define PPROF_T() pp_t = clock64();
+#define PPROF_ACC(v) v += clock64() - pp_t;
+#define PPROF_FLUSH(i) if (lane == 0) { atomicAdd(&g_pprof[i], (unsigned long long)(clock64() - pp_start)); atomicAdd(&g_pprof[i + 1], pp_w0); atomicAdd(&g_pprof[i + 2], pp_w1); atomicAdd(&g_pprof[i + 3], pp_w2); }
+#else
+#define PPROF_VARS
+#define PPROF_T()
+#define PPROF_ACC(v)
+#define PPROF_FLUSH(i)
+#endif
+
 __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) {
     extern __shared__ __align__(128) unsigned char p_smem[];
     const FParams& P = PP.f;
@@ -287,14 +301,17 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
         u32 next_base = 0;
         const u32 grp = PP.grp;
         if (lane == 0) next_base = atomicAdd(P.ticket, grp);
+        PPROF_VARS
         for (u32 itn = 0;; ++itn) {
             const u32 seq = grp * itn + h;
             const u32 slot = seq % P_RING, use = seq / P_RING;
             const u32 base_ticket = __shfl_sync(0xffffffffu, next_base, 0);
             if (lane == 0) next_base = atomicAdd(P.ticket, grp);  // prefetch (harmless past the end)
             const bool act = (u32)h < grp;  // lane groups beyond grp idle
+            PPROF_T()
             if (act && u == 0) mbar_wait_relaxed(smem_u32(&S.freed[slot]), (use & 1u) ^ 1u);
             __syncwarp();
+            PPROF_ACC(pp_w0)
             const u64 tile64 = (u64)base_ticket + h;
             const bool valid = act && tile64 < (u64)P.ntiles;
             const u32 tile = valid ? (u32)tile64 : P_END;
@@ -324,14 +341,20 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             if (act && u == 0) mbar_arrive(smem_u32(&S.ready[slot]));
             if (__ballot_sync(0xffffffffu, act && !valid)) break;  // an END descriptor was published
         }
+        PPROF_FLUSH(8)
     } else if (wid == P_CW + 1) {
         // =========================== T: TMA warp ====================================
+        PPROF_VARS
         for (u32 seq = 0;; ++seq) {
             const u32 slot = seq % P_RING, use = seq / P_RING;
+            PPROF_T()
             mbar_wait_relaxed(smem_u32(&S.ready[slot]), use & 1u);
+            PPROF_ACC(pp_w0)
             const PDesc& D = S.ring[slot];
             const u32 st = seq % P_ST, suse = seq / P_ST;
+            PPROF_T()
             mbar_wait_relaxed(smem_u32(&S.empty[st]), (suse & 1u) ^ 1u);
+            PPROF_ACC(pp_w1)
             PStageInfo& G = S.st[st];
             const u32 tile = D.tile;
             if (tile == P_END) {
@@ -390,11 +413,15 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.freed[slot]));  // descriptor consumed
         }
+        PPROF_FLUSH(4)
     } else if (wid == P_CW + 2) {
         // =========================== O: output warp =================================
+        PPROF_VARS
         for (u32 it = 0;; ++it) {
             const u32 sl = it % P_OS, use = it / P_OS;
+            PPROF_T()
             mbar_wait_relaxed(smem_u32(&S.ofull[sl]), use & 1u);
+            PPROF_ACC(pp_w0)
             const POutSlot& O = S.os[sl];
             const u32 tile = O.tile;
             if (tile == P_END) break;
@@ -407,7 +434,9 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 if (lane >= dlt) incl += v;
             }
             const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+            PPROF_T()
             const u64 base = lookback_exclusive<true, true>(P.status, tile, (u64)total, lane);
+            PPROF_ACC(pp_w1)
             if (lane == 0) {
                 if ((u64)tile == P.tasks[q].tile_base) P.out_off[q] = base;
                 if (tile == P.ntiles - 1) P.out_off[P.ntasks] = base + (u64)total;
@@ -430,12 +459,16 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 mbar_arrive(smem_u32(&S.oempty[sl]));
             }
         }
+        PPROF_FLUSH(12)
     } else {
         // =========================== C: consumer warps ==============================
         u64* s_w = s_work + P_WC * wid;
+        PPROF_VARS
         for (u32 it = 0;; ++it) {
             const u32 st = it % P_ST, suse = it / P_ST;
+            PPROF_T()
             mbar_wait(smem_u32(&S.full[st]), suse & 1u);
+            PPROF_ACC(pp_w0)
             const PStageInfo& G = S.st[st];
             const u32 tile = G.tile;
             const u32 osl = it % P_OS, ouse = it / P_OS;
@@ -561,7 +594,9 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             if (lane == 0) mbar_arrive(smem_u32(&S.empty[st]));
 
             // ---- survivors -> this warp's segment of the output slot -----------------------------
+            PPROF_T()
             mbar_wait_relaxed(smem_u32(&S.oempty[osl]), (ouse & 1u) ^ 1u);
+            PPROF_ACC(pp_w1)
             {
                 u64* od = s_out + (size_t)osl * P_TA + P_WC * wid;
                 const unsigned lt = (1u << lane) - 1u;
@@ -588,6 +623,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.ofull[osl]));
         }
+        PPROF_FLUSH(0)
     }
 }
 
