@@ -188,7 +188,7 @@ extern "C" int dgx_init(int device) {
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * F_TA * sizeof(u64) + kScapMax)));
     CK(cudaFuncSetAttribute(filter_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
-    CK(cudaFuncSetAttribute(mmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * MM_C * sizeof(u64))));
+    CK(cudaFuncSetAttribute(mmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * MM_CP * sizeof(u64))));
     g_num_sms = prop.multiProcessorCount;
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
     if (const char* s = getenv("DGX_MERGE")) g_merge_multi = (strcmp(s, "tree") != 0);
@@ -672,7 +672,7 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     const uint64_t nb = (uint64_t)(max_tiles + 1) * k;
     mplan_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
     CK(cudaGetLastError());
-    mmerge_kernel<<<max_tiles, MM_NT, 2 * MM_C * sizeof(u64), l->stream>>>(P);
+    mmerge_kernel<<<max_tiles, MM_NT, 2 * MM_CP * sizeof(u64), l->stream>>>(P);
     CK(cudaGetLastError());
     mscan_kernel<<<1, 1024, 0, l->stream>>>(P);
     CK(cudaGetLastError());

@@ -31,6 +31,12 @@ constexpr int MM_K = 64;          // maximum fan-in
 constexpr int MM_NT = 512;        // threads per merge CTA
 constexpr int MM_C = 4096;        // values merged in shared memory at once
 constexpr int MM_VT = MM_C / MM_NT;
+// Tile buffers are indexed through mm_pad(): one spare slot per 16 values.  A thread owns MM_VT = 8
+// consecutive outputs, so unpadded 8-byte accesses of a warp sit 16 banks apart (a 16-way conflict on
+// the stores, ~8-way on the data-dependent reads); the padding brings both to the 2-way minimum of
+// 64-bit accesses.
+__device__ __forceinline__ int mm_pad(int i) { return i + (i >> 4); }
+constexpr int MM_CP = MM_C + MM_C / 16 + 2;  // padded buffer length
 
 struct MMParams {
     const MRef* runs;       // k run references (plain arrays or CSR slices of a previous level)
@@ -103,30 +109,32 @@ __device__ __forceinline__ void mm_merge_level(const u64* src, u64* dst, const i
     const int a0 = off[2 * lo];
     const int a1 = (2 * lo + 1 <= nruns) ? off[2 * lo + 1] : a0;
     const int b1 = (2 * lo + 2 <= nruns) ? off[2 * lo + 2] : a1;
-    const u64* A = src + a0;
-    const u64* B = src + a1;
     const int na = a1 - a0, nb = b1 - a1;
     const int d = pos - a0;  // diagonal inside the pair
+#define MM_A(i) src[mm_pad(a0 + (i))]
+#define MM_B(i) src[mm_pad(a1 + (i))]
     int l = d > nb ? d - nb : 0, h = d < na ? d : na;
     while (l < h) {
         const int m = (l + h) >> 1;
-        if (A[m] <= B[d - 1 - m]) l = m + 1; else h = m;
+        if (MM_A(m) <= MM_B(d - 1 - m)) l = m + 1; else h = m;
     }
     int ai = l, bi = d - l;
-    u64 av = ai < na ? A[ai] : kU64Max, bv = bi < nb ? B[bi] : kU64Max;
+    u64 av = ai < na ? MM_A(ai) : kU64Max, bv = bi < nb ? MM_B(bi) : kU64Max;
 #pragma unroll
     for (int s_ = 0; s_ < MM_VT; ++s_) {
         const bool takeA = (bi >= nb) || (ai < na && av <= bv);
-        dst[pos + s_] = takeA ? av : bv;
-        if (takeA) { ++ai; av = ai < na ? A[ai] : kU64Max; }
-        else { ++bi; bv = bi < nb ? B[bi] : kU64Max; }
+        dst[mm_pad(pos + s_)] = takeA ? av : bv;
+        if (takeA) { ++ai; av = ai < na ? MM_A(ai) : kU64Max; }
+        else { ++bi; bv = bi < nb ? MM_B(bi) : kU64Max; }
     }
+#undef MM_A
+#undef MM_B
 }
 
 __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
     extern __shared__ __align__(16) u64 s_mm[];  // two ping-pong buffers of MM_C values
     u64* s_x = s_mm;
-    u64* s_y = s_mm + MM_C;
+    u64* s_y = s_mm + MM_CP;
     __shared__ u64 s_cur[MM_K], s_end[MM_K];
     __shared__ const u64* s_ptr[MM_K];
     __shared__ int s_off[2][MM_K + 2];
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
         for (int r = wid; r < k; r += MM_NT / 32) {
             const int o = s_off[0][r], cnt = s_len[r], slot_n = s_off[0][r + 1] - o;
             const u64* src = s_ptr[r] + s_cur[r];
-            for (int i = lane; i < slot_n; i += 32) s_x[o + i] = i < cnt ? ld_stream(src + i) : kU64Max;
+            for (int i = lane; i < slot_n; i += 32) s_x[mm_pad(o + i)] = i < cnt ? ld_stream(src + i) : kU64Max;
         }
         for (int r = k + tid; r <= MM_K; r += MM_NT) s_off[0][r] = np;  // unused slots are empty runs
         __syncthreads();
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
             int l = 0, h = n;
             while (l < h) {
                 const int m = (l + h) >> 1;
-                if (Z[m] <= bound) l = m + 1; else h = m;
+                if (Z[mm_pad(m)] <= bound) l = m + 1; else h = m;
             }
             nsafe = l;
         }
@@ -283,11 +291,11 @@ __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
             unsigned keep = 0;
             u64 prevv = last;
             bool havep = have_last;
-            if (i0 > 0 && i0 <= nsafe) { prevv = Z[i0 - 1]; havep = true; }
+            if (i0 > 0 && i0 <= nsafe) { prevv = Z[mm_pad(i0 - 1)]; havep = true; }
 #pragma unroll
             for (int j = 0; j < MM_VT; ++j) {
                 if (i0 + j < nsafe) {
-                    const u64 v = Z[i0 + j];
+                    const u64 v = Z[mm_pad(i0 + j)];
                     vals[j] = v;
                     if (!havep || v != prevv) keep |= 1u << j;
                     prevv = v;
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
                 if ((keep >> j) & 1u) st_stream(dst + produced + off++, vals[j]);
             produced += tot_keep;
         }
-        if (nsafe > 0) { last = Z[nsafe - 1]; have_last = true; }
+        if (nsafe > 0) { last = Z[mm_pad(nsafe - 1)]; have_last = true; }
         // ---- advance the runs past everything that was final --------------------------------------
         if (tid < k) {
             const u64 tk = take;  // this run's contribution

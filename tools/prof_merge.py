@@ -18,3 +18,7 @@ for _ in range(3):
 L.sync()
 ms, _ = B.timeit(lambda: L.merge(lists, out, out_len), warm=1, reps=3)
 print("merge ms", ms, "total", tot, "out", int(out_len.item()))
+if os.environ.get("CHECK"):
+    want = torch.unique(torch.cat(lists))
+    n = int(out_len.item())
+    print("check", bool(n == want.numel() and torch.equal(out[:n], want)))
