@@ -157,6 +157,7 @@ struct PStageInfo {            // one stage, produced by T, consumed by C
 };
 struct POutSlot {              // survivors of one tile: warp w owns data[P_WC*w ..) and cnt[w]
     u32 tile, task;
+    u32 first;                 // the tile opens its task's output range (driving offset 0)
     u32 total, arrived;        // running sum of cnt / number of warps that delivered (reset by O)
     u32 cnt[P_CW];
 };
@@ -438,18 +439,23 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             const u64 base = lookback_exclusive<true, true>(P.status, tile, (u64)total, lane);
             PPROF_ACC(pp_w1)
             if (lane == 0) {
-                if ((u64)tile == P.tasks[q].tile_base) P.out_off[q] = base;
+                if (O.first) P.out_off[q] = base;
                 if (tile == P.ntiles - 1) P.out_off[P.ntasks] = base + (u64)total;
             }
             if (base + (u64)total > P.out_cap) {
                 if (lane == 0) atomicExch(P.err, 1);
-            } else {
+            } else if (total != 0) {
+                // a warp's segment holds at most P_WC survivors: P_VA predicated stores per segment,
+                // the shuffles of all segments independent of each other
                 const u64* data = s_out + (size_t)sl * P_TA;
-#pragma unroll 1
+                u64* dst = P.out + base;
+#pragma unroll
                 for (int w = 0; w < P_CW; ++w) {
                     const u32 nw = __shfl_sync(0xffffffffu, cw, w);
                     const u32 ow = __shfl_sync(0xffffffffu, incl, w) - nw;
-                    for (u32 i = lane; i < nw; i += 32) st_stream(P.out + base + ow + i, data[P_WC * w + i]);
+#pragma unroll
+                    for (int r = 0; r < P_VA; ++r)
+                        if ((u32)(lane + 32 * r) < nw) st_stream(dst + ow + lane + 32 * r, data[P_WC * w + lane + 32 * r]);
                 }
             }
             __syncwarp();
@@ -481,6 +487,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 break;
             }
             const u32 na = G.na, k = G.k, q = G.task;
+            const u32 tile_first = G.a0 == 0 ? 1u : 0u;
             const u64* cand = s_A(st) + G.headA;
             const u64* sl = s_SL(st);
             PTile X;
@@ -609,7 +616,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 }
                 if (lane == 0) {
                     O.cnt[wid] = (u32)before;
-                    if (wid == 0) { O.tile = tile; O.task = q; }
+                    if (wid == 0) { O.tile = tile; O.task = q; O.first = tile_first; }
                     // The last warp to deliver publishes the tile's aggregate for the look-back
                     // right away: successors never wait for this CTA's output warp to get here.
                     atomicAdd(&O.total, (u32)before);

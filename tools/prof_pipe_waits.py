@@ -22,10 +22,19 @@ from dgraph_b200 import _lib  # noqa: E402
 def main():
     lib = _lib.load()
     _lib.check(lib.dgx_init(0))
-    raw = C.CDLL(os.environ["DGX_LIB"])
-    raw.dgx_debug_pprof.argtypes = [C.POINTER(C.c_uint64)]
+    raw = C.CDLL(os.environ.get("DGX_LIB", os.path.join(os.path.dirname(_lib.__file__), "libdgx.so")))
+    have_prof = hasattr(raw, "dgx_debug_pprof")  # plain builds: timing only
+    if have_prof:
+        raw.dgx_debug_pprof.argtypes = [C.POINTER(C.c_uint64)]
     Q = int(os.environ.get("Q", "16"))
-    queries = bench.make_queries(Q, 0)
+    if os.environ.get("WORKLOAD", "c2") == "c1":  # C1 batch: 2048 independent 2-way intersections of 1e5-UID lists
+        rng = np.random.default_rng(7)
+        queries = []
+        for _ in range(int(os.environ.get("PAIRS", "2048"))):
+            queries.append([np.unique(rng.integers(0, 10_000_000, 102_000, dtype=np.uint64))[:100_000].copy() for _ in range(2)])
+        Q = len(queries)
+    else:
+        queries = bench.make_queries(Q, 0)
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -49,7 +58,8 @@ def main():
     for _ in range(3):
         step()
     _lib.check(lib.dgx_lane_sync(lane))
-    raw.dgx_debug_pprof(buf)  # clear
+    if have_prof:
+        raw.dgx_debug_pprof(buf)  # clear
     steps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -57,6 +67,9 @@ def main():
         step()
     e1.record(stream)
     _lib.check(lib.dgx_lane_sync(lane))
+    if not have_prof:
+        print(json.dumps({"ms_per_step": e0.elapsed_time(e1) / steps, "workload": os.environ.get("WORKLOAD", "c2")}))
+        return
     raw.dgx_debug_pprof(buf)
     v = [int(x) for x in buf]
     def share(a, b):
