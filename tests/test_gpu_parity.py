@@ -416,6 +416,12 @@ lens = (2_000_000 / np.arange(1, 65)).astype(int)
 big = gen.zipf_gaps(rng, 4_000_000)
 chk([gen.thin(rng, big, min(1.0, l / big.size)) for l in lens], "config-5 shape")
 chk([np.array([2**64 - 1, 2**64 - 1], dtype=np.uint64), np.array([0, 2**64 - 1], dtype=np.uint64), np.array([5], dtype=np.uint64)], "max values")
+# key widths: tiles whose value span fits 32 bits merge on u32 keys, wide ones on u64 -- cover both and the mix
+chk([np.sort(rng.integers(0, 2**64 - 1, 20000, dtype=np.uint64)) for _ in range(9)], "full-range 64-bit values")
+far = (np.arange(30000, dtype=np.uint64) << np.uint64(33)) + np.uint64(12345)
+chk([far[::2], far[1::3], np.arange(5 * 10**9, 5 * 10**9 + 40000, dtype=np.uint64), far[::7]], "wide gaps around a dense cluster")
+edge = np.uint64(2**32 - 2) * np.arange(1, 20001, dtype=np.uint64)
+chk([edge, edge + np.uint64(1), edge[::2] + np.uint64(2**32 - 3)], "spans at the 32-bit boundary")
 print("MULTIWAY_OK")
 '''
     env = dict(os.environ, DGX_MERGE_MULTI_MIN="0")
