@@ -1071,10 +1071,10 @@ extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_u
 #ifdef DGX_PIPE_PROF
 // Experimental builds only (not part of include/dgx.h): read and clear filter_pipe_kernel's wait counters.
 extern "C" int dgx_debug_pprof(uint64_t* out16) {
-    unsigned long long h[16];
+    unsigned long long h[32];
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(h, dgx::g_pprof, sizeof(h)));
-    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    for (int i = 0; i < 32; ++i) out16[i] = h[i];
     memset(h, 0, sizeof(h));
     CK(cudaMemcpyToSymbol(dgx::g_pprof, h, sizeof(h)));
     return DGX_OK;

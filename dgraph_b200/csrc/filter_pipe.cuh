@@ -256,16 +256,24 @@ __device__ __forceinline__ bool phit(const PTile& X, u64 x, int i, unsigned dup,
 
 #ifdef DGX_PIPE_PROF
 // Wait-time breakdown per warp role (cycles, summed over warps / CTAs); experimental builds only.
-__device__ unsigned long long g_pprof[16];
+__device__ unsigned long long g_pprof[32];
 #define PPROF_VARS unsigned long long pp_t = 0, pp_w0 = 0, pp_w1 = 0, pp_w2 = 0; const long long pp_start = clock64();
 #define PPROF_T() pp_t = clock64();
 #define PPROF_ACC(v) v += clock64() - pp_t;
+#define PPROF_PHASE_VARS unsigned long long pp_ph[4] = {0, 0, 0, 0}; long long pp_pt = 0;
+#define PPROF_PHASE_T() pp_pt = clock64();
+#define PPROF_PHASE(k) { const long long n_ = clock64(); pp_ph[k] += n_ - pp_pt; pp_pt = n_; }
+#define PPROF_PHASE_FLUSH() if (lane == 0) { for (int k_ = 0; k_ < 4; ++k_) atomicAdd(&g_pprof[16 + k_], pp_ph[k_]); }
 #define PPROF_FLUSH(i) if (lane == 0) { atomicAdd(&g_pprof[i], (unsigned long long)(clock64() - pp_start)); atomicAdd(&g_pprof[i + 1], pp_w0); atomicAdd(&g_pprof[i + 2], pp_w1); atomicAdd(&g_pprof[i + 3], pp_w2); }
 #else
 #define PPROF_VARS
 #define PPROF_T()
 #define PPROF_ACC(v)
 #define PPROF_FLUSH(i)
+#define PPROF_PHASE_VARS
+#define PPROF_PHASE_T()
+#define PPROF_PHASE(k)
+#define PPROF_PHASE_FLUSH()
 #endif
 
 __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) {
@@ -470,11 +478,13 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
         // =========================== C: consumer warps ==============================
         u64* s_w = s_work + P_WC * wid;
         PPROF_VARS
+        PPROF_PHASE_VARS
         for (u32 it = 0;; ++it) {
             const u32 st = it % P_ST, suse = it / P_ST;
             PPROF_T()
             mbar_wait(smem_u32(&S.full[st]), suse & 1u);
             PPROF_ACC(pp_w0)
+            PPROF_PHASE_T()
             const PStageInfo& G = S.st[st];
             const u32 tile = G.tile;
             const u32 osl = it % P_OS, ouse = it / P_OS;
@@ -516,6 +526,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             const u32 nstaged = G.nstaged < km1 ? G.nstaged : km1;
 
             u32 t = 0;
+            PPROF_PHASE(0)
             while (t < km1 && rows > 0) {
                 if (t < nstaged) {
                     if (rows == 2 || t + 1 >= nstaged) {
@@ -595,6 +606,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 }
             }
             if (rows == 0) alive = 0;
+            PPROF_PHASE(1)
 
             // ---- this warp is done with the stage: hand it back to T ---------------------------
             __syncwarp();
@@ -604,6 +616,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             PPROF_T()
             mbar_wait_relaxed(smem_u32(&S.oempty[osl]), (ouse & 1u) ^ 1u);
             PPROF_ACC(pp_w1)
+            PPROF_PHASE_T()
             {
                 u64* od = s_out + (size_t)osl * P_TA + P_WC * wid;
                 const unsigned lt = (1u << lane) - 1u;
@@ -629,8 +642,10 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.ofull[osl]));
+            PPROF_PHASE(2)
         }
         PPROF_FLUSH(0)
+        PPROF_PHASE_FLUSH()
     }
 }
 

@@ -54,7 +54,7 @@ def main():
     def step():
         _lib.check(lib.dgx_dev_filter_batch(lane, _lib.OP_INTERSECT, c_ptrs, c_lens, c_koff, Q,
                                             C.c_void_p(d_out.data_ptr()), out_cap, C.c_void_p(d_off.data_ptr())))
-    buf = (C.c_uint64 * 16)()
+    buf = (C.c_uint64 * 32)()
     for _ in range(3):
         step()
     _lib.check(lib.dgx_lane_sync(lane))
@@ -80,6 +80,8 @@ def main():
         "tma_warp": {"wait_descriptor": share(v[5], v[4]), "wait_stage_empty": share(v[6], v[4])},
         "metadata_warp": {"wait_ring_slot": share(v[9], v[8])},
         "output_warp": {"wait_slot_full": share(v[13], v[12]), "look_back": share(v[14], v[12])},
+        "consumer_phases": {"tile_setup": share(v[16], v[0]), "list_searches": share(v[17], v[0]),
+                            "deliver_survivors": share(v[18], v[0])},
         "raw_cycles": v,
     }
     print(json.dumps(out))
