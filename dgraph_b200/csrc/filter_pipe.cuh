@@ -43,7 +43,10 @@ constexpr int P_NT = P_CT + 96;          // + metadata warp + TMA warp + output 
 constexpr int P_VA = 2;                  // candidate rows per consumer warp
 constexpr int P_WC = 32 * P_VA;          // candidates per consumer warp
 constexpr int P_TA = P_CW * 64;          // candidates per tile
-constexpr int P_OS = 4;                  // output slots in flight
+#ifndef DGX_P_OS
+#define DGX_P_OS 6
+#endif
+constexpr int P_OS = DGX_P_OS;           // output slots in flight (6 vs 4: 2-list batches +4.5 %, C2 unchanged)
 #ifndef DGX_P_ST
 #define DGX_P_ST 2
 #endif
