@@ -12,7 +12,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --e2e-steps 1 > $o/${tag}_ncu_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:filter_pipe_kernel -s 3 -c 1 -f -o $o/${tag}_pipe \
     python bench.py --steps 3 --warmup 3 --e2e-steps 1 > $o/${tag}_ncu_pipe.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $o/${tag}_merge_launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(msample|mplan|mmerge|mscan|mcompact|merge)_kernel' -c 60 --csv --log-file $o/${tag}_merge_launches.csv \
     python tools/prof_merge.py 100000000 > $o/${tag}_ncu_merge.log 2>&1
 for w in c2 c1; do
   WORKLOAD=$w PAIRS=1024 DGX_LIB=$PWD/dgraph_b200/libdgx_prof.so timeout 150 python tools/prof_pipe_waits.py > $o/${tag}_pipe_waits_$w.json 2>> $o/${tag}_pw.err
