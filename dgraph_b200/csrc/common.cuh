@@ -138,7 +138,7 @@ constexpr u64 kValMask = (1ull << 62) - 1;
 // Returns the exclusive prefix of the tile (same value in every lane).
 // kPublished: the tile's aggregate word has already been stored by someone else.
 // kBackoff: sleep between polls (the caller is a helper warp that must not steal issue slots).
-template <bool kPublished = false, bool kBackoff = false>
+template <bool kPublished = false, unsigned kBackoff = 0>  // kBackoff: ns to sleep between polls (0 = spin)
 __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 aggregate, int lane) {
     if (tile == 0) {
         if (lane == 0) st_relaxed(status, kFlagPrefix | aggregate);
@@ -151,7 +151,7 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* status, u32 tile, u64 agg
         long long my = idx - lane;
         u64 w;
         if (my >= 0) {
-            while (((w = ld_relaxed(status + my)) >> 62) == 0) { if (kBackoff) __nanosleep(100); }
+            while (((w = ld_relaxed(status + my)) >> 62) == 0) { if (kBackoff) __nanosleep(kBackoff); }
         } else {
             w = kFlagPrefix;  // virtual tile before the first: prefix 0
         }

@@ -118,6 +118,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
 
 // Same wait for the pipeline's helper warps: the try_wait carries a suspend-time hint and a miss
 // backs off with nanosleep, so a waiting warp does not compete with working warps for issue slots.
+template <unsigned kSleepNs = 128>
 __device__ __forceinline__ void mbar_wait_relaxed(u32 bar, u32 parity) {
     u32 done = 0;
     while (true) {
@@ -128,7 +129,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(u32 bar, u32 parity) {
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
         if (done) break;
-        __nanosleep(128);
+        __nanosleep(kSleepNs);
     }
 }
 
