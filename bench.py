@@ -214,20 +214,19 @@ def main():
     out_cap = sum(min(l.size for l in qq) for qq in queries)
     d_out = torch.empty(out_cap + 2, dtype=torch.int64, device=dev)
     d_off = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+    # N > 1: the all-gatherv is ONE collective per step over preallocated buffers -- every rank sends
+    # [count | results padded to a static bound] (no host sync, no per-step allocation).  It runs in
+    # stream order after the filter launch (~25 us at N = 2).
+    pad = min(int(out_cap), 1 << 16)
+    send = torch.empty(1 + pad, dtype=torch.int64, device=dev)
+    gathered = torch.empty(world * (1 + pad), dtype=torch.int64, device=dev)
 
     def step():
         _lib.check(lib.dgx_dev_filter_batch(lane, _lib.OP_INTERSECT, c_ptrs, c_lens, c_koff, Q,
                                             C.c_void_p(d_out.data_ptr()), out_cap, C.c_void_p(d_off.data_ptr())))
-        if world > 1:  # all-gatherv of the results: counts, then payloads padded to the max count
-            cnt = d_off[Q:Q + 1].clone()
-            counts = torch.empty(world, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(counts, cnt)
-            mx = int(out_cap)  # static bound: no host sync inside the step
-            pad = min(mx, 1 << 16)
-            gathered = torch.empty(world * pad, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gathered, d_out[:pad].contiguous())
-            return counts, gathered
-        return None
+        if world > 1:
+            torch.cat((d_off[Q:Q + 1], d_out[:pad]), out=send)
+            dist.all_gather_into_tensor(gathered, send)
 
     # ---- parity check (outside the timed region) ------------------------------------
     from oracle import pyoracle as orc
@@ -241,6 +240,10 @@ def main():
     bit_exact = bool(np.array_equal(res[int(off[0]):int(off[1])], want0)
                      and np.array_equal(res[int(off[Q - 1]):int(off[Q])], wantl))
     out_uids = int(off[Q])
+    if world > 1:  # the gathered block of this rank must be its own [count | results]
+        mine = gathered[rank * (1 + pad):(rank + 1) * (1 + pad)].cpu().numpy().view(np.uint64)
+        npay = min(out_uids, pad)
+        bit_exact = bit_exact and int(mine[0]) == out_uids and bool(np.array_equal(mine[1:1 + npay], res[:npay]))
 
     # ---- device-resident timing --------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -248,8 +251,6 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     for _ in range(200):  # NVML init can take a while when 8 ranks start at once
         if sampler.ok or hasattr(sampler, "err"):
             break
@@ -257,11 +258,18 @@ def main():
     sampler.active = True
     launches0 = lib.dgx_lane_launches(lane)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # barrier + synchronize immediately before the first timed launch: a rank that enters the loop late
+    # (even by one 10 ms sleep above) would make its peers' first gather wait inside their timed region
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     evs[0].record()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         step()
         evs[i + 1].record()
+    host_submit_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps  # host time to enqueue one step
     torch.cuda.synchronize()
     sampler.active = False
     if world > 1:
@@ -386,7 +394,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(Q, world),
-            "bit_exact": bit_exact, "out_uids_per_step": out_uids,
+            "bit_exact": bit_exact, "out_uids_per_step": out_uids, "host_submit_ms_per_step": round(host_submit_ms, 4),
+            "step_ms_rank0": {"median": round(float(np.median(step_ms)), 4), "p10": round(float(np.percentile(step_ms, 10)), 4),
+                              "p90": round(float(np.percentile(step_ms, 90)), 4), "max": round(float(np.max(step_ms)), 4)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_all, "clocks": clocks,
         }
