@@ -7,5 +7,5 @@ timeout 120 python bench.py --e2e-steps 1 > gpurun_out/${tag}_bench.json 2> gpur
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/${tag}_bench.json").read().strip().splitlines()[-1])
-print("value %.4g ms %.4f frac %.3f bit_exact %s"%(d["value"],d["ms_per_step"],d["roofline"]["frac"],d["config"].get("bit_exact")))
+print("value %.4g ms %.4f frac %.3f bit_exact %s"%(d["value"],d["ms_per_step"],d["roofline"]["frac"],d.get("bit_exact")))
 PY
