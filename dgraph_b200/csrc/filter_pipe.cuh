@@ -4,26 +4,29 @@
 // Difference over a batch of queries, bit-exact incl. duplicate semantics), built
 // as a Blackwell pipeline:
 //
-//   filter_plan_kernel   one warp per (tile, filter list): both slice bounds
+//   filter_tiles_kernel  one thread per tile: owning task, driving offset, plan index,
+//                        predecessor value -> a tile table in HBM.
+//   filter_plan_kernel   one thread per (tile, filter list): both slice bounds
 //                        [lower_bound(L_j, tile first), upper_bound(L_j, tile last))
-//                        with interleaved 32-ary searches -> a small plan in HBM.
-//   filter_pipe_kernel   persistent CTAs (grid = resident capacity).  Warp roles:
-//     M  (1 warp)  metadata: claims the next tile (atomic ticket = look-back order),
-//                  resolves its task, list descriptors and plan entries and pushes a
+//                        as two interleaved binary searches -> a small plan in HBM.
+//   filter_pipe_kernel   persistent CTAs (grid = resident capacity, 2 per SM).  Warp roles:
+//     M  (1 warp)  metadata: claims the next tile(s) (atomic ticket = look-back order),
+//                  reads the tile table, list descriptors and plan entries and pushes a
 //                  tile descriptor into a small ring in shared memory;
 //     T  (1 warp)  waits for a free stage, lays the tile's slices out and issues ONE
 //                  TMA bulk copy (cp.async.bulk, mbarrier complete_tx) per list plus
-//                  one for the 1024 driving values: global -> shared with no
+//                  one for the 512 driving values: global -> shared with no
 //                  register staging and no consumer instruction spent on loads;
-//     C (16 warps) consume a stage, each warp on its own 64 candidates (2 rows in
+//     C  (8 warps) consume a stage, each warp on its own 64 candidates (2 rows in
 //                  registers) and with NO block barrier: binary-lifting searches over
 //                  the staged 64-bit keys, interleaved across rows / lists for ILP,
 //                  warp-level re-packs between lists, survivors dropped into the
-//                  warp's fixed segment of an output slot;
-//     O  (1 warp)  drains output slots: tile count -> decoupled look-back -> ordered
-//                  stores.  Only this warp ever waits on other CTAs.
-//   Two stages and two output slots are in flight per CTA, so the TMA traffic of
-//   tile i+1 and the look-back of tile i-1 overlap the searches of tile i.
+//                  warp's fixed segment of an output slot; the last warp to deliver a
+//                  tile publishes the tile's aggregate for the look-back;
+//     O  (1 warp)  drains output slots: decoupled look-back -> ordered stores.  Only
+//                  this warp ever waits on other CTAs.
+//   Two stages and six output slots are in flight per CTA, so the TMA traffic of
+//   tile i+1 and the look-back of tiles i-1.. overlap the searches of tile i.
 //
 // Lists that are not pre-staged (slice larger than the stage, or more than 8
 // filter lists) are binary-searched in HBM by the surviving candidates.
@@ -317,9 +320,9 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
 
     if (wid == P_CW) {
         // =========================== M: metadata warp ===============================
-        // Four tiles per iteration (eight lanes each), claimed with ONE atomic so a CTA's tiles
-        // stay in look-back order; the ticket for the next iteration is fetched before this
-        // iteration's loads, so the chain per group is two global latencies: tile table ->
+        // PP.grp (1 .. P_GRP) tiles per iteration, eight lanes each, claimed with ONE atomic so a
+        // CTA's tiles stay in look-back order; the ticket for the next iteration is fetched before
+        // this iteration's loads, so the chain per group is two global latencies: tile table ->
         // {list descriptors, plan entries}.  Sub-lane u < 8 resolves filter list u of its tile.
         const int h = lane >> 3, u = lane & 7;
         u32 next_base = 0;
