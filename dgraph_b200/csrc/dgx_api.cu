@@ -139,6 +139,11 @@ struct HostArena {
         c.used += bytes;
         return DGX_OK;
     }
+    size_t used_bytes() const {
+        size_t t = 0;
+        for (const auto& c : chunks) t += c.used;
+        return t;
+    }
     void reset() {  // keep the largest (last) chunk
         while (chunks.size() > 1) {
             cudaFreeHost(chunks.front().p);
@@ -163,6 +168,21 @@ struct dgx_lane {
     uint64_t* h_word = nullptr;  // pinned scratch for lengths (8 words)
     uint64_t launches = 0;
 };
+
+// Start of a device-level op on a lane: bind the device, recycle the workspace.  The pinned descriptor
+// staging is only recycled at a lane sync (queued H2D copies read from it); a caller that queues thousands
+// of ops without ever syncing would grow it without bound, so past a soft cap the op syncs the stream itself.
+constexpr size_t kHostArenaSoftCap = size_t(16) << 20;
+static int lane_begin_op(dgx_lane* l) {
+    CK(cudaSetDevice(l->device));
+    if (l->host.used_bytes() > kHostArenaSoftCap) {
+        CK(cudaStreamSynchronize(l->stream));
+        l->host.reset();
+        l->ws.release_retired();
+    }
+    l->ws.reset();
+    return DGX_OK;
+}
 
 // ---------------------------------------------------------------------------
 // lifecycle
@@ -277,10 +297,12 @@ extern "C" void dgx_lane_destroy(dgx_lane* l) {
     delete l;
 }
 
-extern "C" void* dgx_lane_stream(dgx_lane* l) { return (void*)l->stream; }
-extern "C" uint64_t dgx_lane_launches(const dgx_lane* l) { return l->launches; }
+extern "C" void* dgx_lane_stream(dgx_lane* l) { return l ? (void*)l->stream : nullptr; }
+extern "C" uint64_t dgx_lane_launches(const dgx_lane* l) { return l ? l->launches : 0; }
 
 extern "C" int dgx_lane_sync(dgx_lane* l) {
+    if (!l) return fail(DGX_ERR_ARG, "null lane");
+    CK(cudaSetDevice(l->device));
     CK(cudaMemcpyAsync(l->h_err, l->d_err, sizeof(int), cudaMemcpyDeviceToHost, l->stream));
     CK(cudaStreamSynchronize(l->stream));
     l->host.reset();
@@ -303,11 +325,15 @@ extern "C" void dgx_dev_free(void* p) {
     if (p) cudaFree(p);
 }
 extern "C" int dgx_memcpy_h2d(dgx_lane* l, void* d, const void* h, size_t bytes) {
+    if (!l) return fail(DGX_ERR_ARG, "null lane");
+    CK(cudaSetDevice(l->device));
     if (bytes) CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, l->stream));
     g_stats.h2d += bytes;
     return DGX_OK;
 }
 extern "C" int dgx_memcpy_d2h(dgx_lane* l, void* h, const void* d, size_t bytes) {
+    if (!l) return fail(DGX_ERR_ARG, "null lane");
+    CK(cudaSetDevice(l->device));
     if (bytes) CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, l->stream));
     g_stats.d2h += bytes;
     return DGX_OK;
@@ -462,8 +488,7 @@ extern "C" int dgx_dev_filter_batch(dgx_lane* l, int op, const uint64_t* const* 
                                     const size_t* k_off, size_t nq, uint64_t* d_out, size_t out_cap,
                                     uint64_t* d_out_off) {
     if (!l || (op != DGX_OP_INTERSECT && op != DGX_OP_DIFFERENCE)) return fail(DGX_ERR_ARG, "bad lane/op");
-    CK(cudaSetDevice(l->device));
-    l->ws.reset();
+    if (int rc = lane_begin_op(l)) return rc;
     const size_t nlists = nq ? k_off[nq] : 0;
     std::vector<ListDesc> ld(nlists);
     for (size_t i = 0; i < nlists; ++i) ld[i] = {d_lists[i], lens[i], nullptr};
@@ -686,8 +711,7 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
 extern "C" int dgx_dev_merge_sorted(dgx_lane* l, const uint64_t* const* d_lists, const size_t* lens, size_t k,
                                     uint64_t* d_out, size_t out_cap, uint64_t* d_out_len) {
     if (!l) return fail(DGX_ERR_ARG, "null lane");
-    CK(cudaSetDevice(l->device));
-    l->ws.reset();
+    if (int rc = lane_begin_op(l)) return rc;
     std::vector<ListDesc> ld(k);
     for (size_t i = 0; i < k; ++i) ld[i] = {d_lists[i], lens[i], nullptr};
     g_stats.calls += 1;
@@ -802,8 +826,7 @@ static int decode_impl(dgx_lane* l, const DPack& pk, uint64_t seek, uint64_t* d_
 extern "C" int dgx_dev_decode(dgx_lane* l, const dgx_dev_pack* pk, uint64_t seek, uint64_t* d_out, size_t out_cap,
                               uint64_t* d_out_len) {
     if (!l || !pk) return fail(DGX_ERR_ARG, "null argument");
-    CK(cudaSetDevice(l->device));
-    l->ws.reset();
+    if (int rc = lane_begin_op(l)) return rc;
     g_stats.calls += 1;
     g_stats.uids_in += pk->exact_len;
     return decode_impl(l, pk->pk, seek, d_out, out_cap, d_out_len);
