@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS ?= -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-maybe-uninitialized -Xptxas -v
 CSRC := dgraph_b200/csrc
-HDRS := $(wildcard $(CSRC)/*.cuh) include/dgx.h
+HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/dgx.h
 
 all: dgraph_b200/libdgx.so oracle/liboracle.so
 

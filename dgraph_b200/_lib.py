@@ -74,6 +74,11 @@ SYMBOLS = {
     "dgx_dev_pack_exact_len": (_sz, [_vp]),
     "dgx_dev_pack_bytes": (_sz, [_vp]),
     "dgx_dev_decode": (_int, [_vp, _vp, _u64, _vp, _sz, _vp]),
+    "dgx_wire_posting_list_pack": (_int, [_vp, _sz, C.POINTER(_vp), _szp]),
+    "dgx_wire_pack_measure": (_int, [_vp, _sz, _szp, _szp]),
+    "dgx_wire_pack_parse": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _sz, C.POINTER(PackView)]),
+    "dgx_wire_list_header": (_sz, [_sz, _vp]),
+    "dgx_wire_list_decode": (_int, [_vp, _sz, _vp, _sz, _szp]),
 }
 
 _lib = None

@@ -23,6 +23,7 @@
 #include "filter_pipe.cuh"
 #include "merge_kernel.cuh"
 #include "merge_multi.cuh"
+#include "wire.hpp"
 
 using namespace dgx;
 
@@ -1089,6 +1090,102 @@ extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_u
     const uint64_t* lists[1] = {v};
     const size_t lens[1] = {m};
     return dgx_decode_intersect_sorted(p, after_uid, lists, lens, 1, out, out_cap, out_len);
+}
+
+// ---------------------------------------------------------------------------
+// protobuf wire-format adjacency (host only; see include/dgx.h and wire.hpp)
+// ---------------------------------------------------------------------------
+extern "C" int dgx_wire_posting_list_pack(const uint8_t* buf, size_t len, const uint8_t** pack, size_t* pack_len) {
+    if ((!buf && len) || !pack || !pack_len) return fail(DGX_ERR_ARG, "null argument");
+    *pack = nullptr;
+    *pack_len = 0;
+    wire::Reader r{buf, buf + len};
+    uint32_t f, wt;
+    bool ok, seen = false;
+    while (r.tag(&f, &wt, &ok)) {
+        if (f == 1 && wt == 2) {
+            // a sub-message split over several occurrences would have to be merged; no encoder emits that
+            if (seen) return fail(DGX_ERR_ARG, "pb.PostingList.pack occurs more than once");
+            if (!r.bytes(pack, pack_len)) return fail(DGX_ERR_ARG, "truncated pb.PostingList");
+            seen = true;
+        } else if (!r.skip(wt, f)) {
+            return fail(DGX_ERR_ARG, "malformed pb.PostingList");
+        }
+    }
+    if (!ok) return fail(DGX_ERR_ARG, "malformed pb.PostingList");
+    return DGX_OK;
+}
+
+extern "C" int dgx_wire_pack_measure(const uint8_t* buf, size_t len, size_t* nblocks, size_t* delta_bytes) {
+    if ((!buf && len) || !nblocks || !delta_bytes) return fail(DGX_ERR_ARG, "null argument");
+    uint32_t bs;
+    if (!wire::walk_pack(buf, len, &bs, nblocks, delta_bytes, nullptr)) return fail(DGX_ERR_ARG, "malformed pb.UidPack");
+    return DGX_OK;
+}
+
+extern "C" int dgx_wire_pack_parse(const uint8_t* buf, size_t len, uint64_t* base, uint32_t* num_uids,
+                                   uint64_t* delta_off, uint8_t* deltas, size_t nblocks_cap, size_t delta_cap,
+                                   dgx_pack_view* view) {
+    if ((!buf && len) || !view || !delta_off) return fail(DGX_ERR_ARG, "null argument");
+    uint32_t bs;
+    size_t nb, db;
+    if (!wire::walk_pack(buf, len, &bs, &nb, &db, nullptr)) return fail(DGX_ERR_ARG, "malformed pb.UidPack");
+    if (nb > nblocks_cap || db > delta_cap)
+        return fail(DGX_ERR_CAP, "pb.UidPack has %zu blocks / %zu delta bytes, arrays hold %zu / %zu", nb, db, nblocks_cap, delta_cap);
+    if ((nb && (!base || !num_uids)) || (db && !deltas)) return fail(DGX_ERR_ARG, "null array");
+    const wire::PackArrays a{base, num_uids, delta_off, deltas};
+    wire::walk_pack(buf, len, &bs, &nb, &db, &a);
+    view->block_size = bs;
+    view->nblocks = nb;
+    view->base = base;
+    view->num_uids = num_uids;
+    view->delta_off = delta_off;
+    view->deltas = deltas;
+    return DGX_OK;
+}
+
+extern "C" size_t dgx_wire_list_header(size_t n, uint8_t* hdr) {
+    if (n == 0 || !hdr) return 0;
+    size_t w = 0;
+    hdr[w++] = 0x0A;  // field 1, wire type 2
+    uint64_t v = (uint64_t)n * 8u;
+    while (v >= 0x80) { hdr[w++] = (uint8_t)(v | 0x80); v >>= 7; }
+    hdr[w++] = (uint8_t)v;
+    return w;
+}
+
+extern "C" int dgx_wire_list_decode(const uint8_t* buf, size_t len, uint64_t* out, size_t out_cap, size_t* out_len) {
+    if ((!buf && len) || !out_len) return fail(DGX_ERR_ARG, "null argument");
+    wire::Reader r{buf, buf + len};
+    uint32_t f, wt;
+    bool ok;
+    size_t n = 0;
+    while (r.tag(&f, &wt, &ok)) {
+        if (f == 1 && wt == 2) {
+            const uint8_t* s;
+            size_t nbytes;
+            if (!r.bytes(&s, &nbytes) || (nbytes & 7)) return fail(DGX_ERR_ARG, "malformed pb.List");
+            const size_t cnt = nbytes / 8;
+            if (out) {
+                if (n + cnt > out_cap) return fail(DGX_ERR_CAP, "pb.List does not fit out_cap (%zu)", out_cap);
+                memcpy(out + n, s, nbytes);  // fixed64 is little-endian on the wire, like the hosts this runs on
+            }
+            n += cnt;
+        } else if (f == 1 && wt == 1) {
+            if (r.end - r.p < 8) return fail(DGX_ERR_ARG, "truncated pb.List");
+            if (out) {
+                if (n + 1 > out_cap) return fail(DGX_ERR_CAP, "pb.List does not fit out_cap (%zu)", out_cap);
+                memcpy(out + n, r.p, 8);
+            }
+            r.p += 8;
+            n += 1;
+        } else if (!r.skip(wt, f)) {
+            return fail(DGX_ERR_ARG, "malformed pb.List");
+        }
+    }
+    if (!ok) return fail(DGX_ERR_ARG, "malformed pb.List");
+    *out_len = n;
+    return DGX_OK;
 }
 
 #ifdef DGX_PIPE_PROF

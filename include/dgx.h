@@ -136,6 +136,42 @@ int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek,
 int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
                              uint64_t* out, size_t out_cap, size_t* out_len);
 
+/* ---- protobuf wire-format adjacency (host only, no device needed) ----------- */
+/* Posting lists reach the path as serialized pb.PostingList values read from Badger
+ * (proto.Unmarshal, posting/list.go:1045, posting/mvcc.go:634) and leave it as pb.List
+ * inside pb.Result.uid_matrix (protos/pb.proto:22-24, 76-78).  These entry points read
+ * and write exactly those bytes, so a caller can go from a stored value to dgx_pack_view
+ * and from a result buffer to a pb.List message without building Go structs in between.
+ * Standard proto3 wire format; unknown fields are skipped; malformed or truncated input
+ * is DGX_ERR_ARG. */
+
+/* pb.PostingList{pack = 1} (protos/pb.proto:402-408): locate the serialized pb.UidPack
+ * inside a stored value.  *pack == NULL, *pack_len == 0 when the field is absent (nil pack). */
+int dgx_wire_posting_list_pack(const uint8_t* buf, size_t len, const uint8_t** pack, size_t* pack_len);
+
+/* pb.UidPack{block_size = 1, blocks = 2, alloc_ref = 23} / pb.UidBlock{base = 1,
+ * deltas = 2, num_uids = 3} (protos/pb.proto:378-400): count blocks and delta bytes so
+ * the caller can allocate the struct of arrays. */
+int dgx_wire_pack_measure(const uint8_t* buf, size_t len, size_t* nblocks, size_t* delta_bytes);
+
+/* Parse the same message into caller-allocated arrays (base[nblocks], num_uids[nblocks],
+ * delta_off[nblocks + 1], deltas[delta_bytes]) and point `view` at them: the result feeds
+ * dgx_decode / dgx_intersect_compressed / dgx_dev_pack_upload directly.  DGX_ERR_CAP when
+ * the arrays are too small. */
+int dgx_wire_pack_parse(const uint8_t* buf, size_t len,
+                        uint64_t* base, uint32_t* num_uids, uint64_t* delta_off, uint8_t* deltas,
+                        size_t nblocks_cap, size_t delta_cap, dgx_pack_view* view);
+
+/* pb.List{repeated fixed64 uids = 1} (protos/pb.proto:22-24) is packed: tag 0x0A, varint
+ * byte length, then the little-endian values -- a result buffer IS the payload.  Writes the
+ * header for n values into hdr (at most 11 bytes) and returns its length; 0 for n == 0
+ * (proto3 omits an empty repeated field).  The message is hdr || values. */
+size_t dgx_wire_list_header(size_t n, uint8_t* hdr);
+
+/* Inverse: the uids of a serialized pb.List, packed chunks and unpacked entries in order.
+ * out == NULL only counts.  DGX_ERR_CAP when out_cap is too small. */
+int dgx_wire_list_decode(const uint8_t* buf, size_t len, uint64_t* out, size_t out_cap, size_t* out_len);
+
 /* ---- device-resident API ------------------------------------------------- */
 /* For callers that keep posting lists in HBM (a pack / list cache) and for
  * roofline measurement.  All pointers named d_* are device pointers on the
