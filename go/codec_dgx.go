@@ -74,3 +74,52 @@ func Decode(pack *pb.UidPack, seek uint64) []uint64 {
 	}
 	return out[:int(outLen)]
 }
+
+// DecodeStored decodes the uids of a posting list straight from its stored bytes (the
+// value proto.Unmarshal receives at posting/list.go:1045): the pb.UidPack inside the
+// serialized pb.PostingList is parsed into the struct-of-arrays view by libdgx itself
+// (dgx_wire_*), so no []*pb.UidBlock is ever built.  New entry point (not in the
+// reference); nil for a posting list without a pack.
+func DecodeStored(value []byte, seek uint64) ([]uint64, bool) {
+	if len(value) == 0 {
+		return []uint64{}, true
+	}
+	buf := (*C.uint8_t)(unsafe.Pointer(&value[0]))
+	var sub *C.uint8_t
+	var subLen C.size_t
+	if C.dgx_wire_posting_list_pack(buf, C.size_t(len(value)), &sub, &subLen) != C.DGX_OK {
+		return nil, false
+	}
+	if sub == nil {
+		return []uint64{}, true
+	}
+	var nb, db C.size_t
+	if C.dgx_wire_pack_measure(sub, subLen, &nb, &db) != C.DGX_OK {
+		return nil, false
+	}
+	base := C.malloc(nb*8 + 8)
+	num := C.malloc(nb*4 + 4)
+	off := C.malloc(nb*8 + 16)
+	del := C.malloc(db + 16)
+	defer func() { C.free(base); C.free(num); C.free(off); C.free(del) }()
+	var view C.dgx_pack_view
+	if C.dgx_wire_pack_parse(sub, subLen, (*C.uint64_t)(base), (*C.uint32_t)(num), (*C.uint64_t)(off),
+		(*C.uint8_t)(del), nb, db, &view) != C.DGX_OK {
+		return nil, false
+	}
+	n := 0
+	nums := (*[1 << 28]C.uint32_t)(num)[:int(nb):int(nb)]
+	for _, c := range nums {
+		n += int(c) // codec.ExactLen
+	}
+	out := make([]uint64, n)
+	var outLen C.size_t
+	var outPtr *C.uint64_t
+	if n > 0 {
+		outPtr = (*C.uint64_t)(unsafe.Pointer(&out[0]))
+	}
+	if C.dgx_decode(&view, C.uint64_t(seek), outPtr, C.size_t(n), &outLen) != C.DGX_OK {
+		return nil, false
+	}
+	return out[:int(outLen)], true
+}
