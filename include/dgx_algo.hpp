@@ -147,4 +147,53 @@ inline std::vector<uint64_t> Decode(const pb::UidPack* p, uint64_t seek) {
 }
 
 }  // namespace codec
+
+// Wire-format adjacency (dgx_wire_*, host only): the bytes proto.Unmarshal sees at posting/list.go:1045 and
+// the pb.List messages of pb.Result.uid_matrix (protos/pb.proto:22-24, 76-78).
+namespace wire {
+
+// Serialized pb.UidPack -> the struct-of-arrays pb::UidPack.
+inline pb::UidPack ParseUidPack(const uint8_t* buf, size_t len) {
+    size_t nb = 0, db = 0;
+    check(dgx_wire_pack_measure(buf, len, &nb, &db));
+    pb::UidPack p;
+    p.base.resize(nb);
+    p.num_uids.resize(nb);
+    p.delta_off.assign(nb + 1, 0);
+    p.deltas.resize(db);
+    dgx_pack_view v;
+    check(dgx_wire_pack_parse(buf, len, p.base.data(), p.num_uids.data(), p.delta_off.data(), p.deltas.data(), nb, db, &v));
+    p.block_size = v.block_size;
+    return p;
+}
+
+// Serialized pb.PostingList -> its pb.UidPack; `found` is false when the posting list has no pack (nil).
+inline pb::UidPack PostingListPack(const uint8_t* buf, size_t len, bool* found) {
+    const uint8_t* sub = nullptr;
+    size_t sub_len = 0;
+    check(dgx_wire_posting_list_pack(buf, len, &sub, &sub_len));
+    if (found) *found = sub != nullptr;
+    return sub ? ParseUidPack(sub, sub_len) : pb::UidPack();
+}
+
+// pb.List -> its serialized message (header followed by the little-endian uids).
+inline std::vector<uint8_t> ListToWire(const pb::List& l) {
+    uint8_t hdr[16];
+    const size_t h = dgx_wire_list_header(l.Uids.size(), hdr);
+    std::vector<uint8_t> out(h + l.Uids.size() * 8);
+    std::copy(hdr, hdr + h, out.begin());
+    if (!l.Uids.empty()) std::copy((const uint8_t*)l.Uids.data(), (const uint8_t*)l.Uids.data() + l.Uids.size() * 8, out.begin() + h);
+    return out;
+}
+
+inline pb::List ListFromWire(const uint8_t* buf, size_t len) {
+    size_t n = 0;
+    check(dgx_wire_list_decode(buf, len, nullptr, 0, &n));
+    pb::List l;
+    l.Uids.resize(n);
+    if (n) check(dgx_wire_list_decode(buf, len, l.Uids.data(), n, &n));
+    return l;
+}
+
+}  // namespace wire
 }  // namespace dgx
