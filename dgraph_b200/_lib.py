@@ -78,6 +78,7 @@ SYMBOLS = {
     "dgx_wire_pack_measure": (_int, [_vp, _sz, _szp, _szp]),
     "dgx_wire_pack_parse": (_int, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _sz, C.POINTER(PackView)]),
     "dgx_wire_list_header": (_sz, [_sz, _vp]),
+    "dgx_wire_uid_matrix": (_int, [_vp, _vp, _sz, _vp, _sz, _szp]),
     "dgx_wire_list_decode": (_int, [_vp, _sz, _vp, _sz, _szp]),
 }
 

@@ -1154,6 +1154,36 @@ extern "C" size_t dgx_wire_list_header(size_t n, uint8_t* hdr) {
     return w;
 }
 
+extern "C" int dgx_wire_uid_matrix(const uint64_t* out, const uint64_t* out_off, size_t nrows, uint8_t* buf, size_t buf_cap,
+                                   size_t* len) {
+    if (!len || (nrows && !out_off)) return fail(DGX_ERR_ARG, "null argument");
+    auto varint_len = [](uint64_t v) { size_t n = 1; while (v >= 0x80) { v >>= 7; ++n; } return n; };
+    auto put_varint = [](uint8_t* p, uint64_t v) { size_t n = 0; while (v >= 0x80) { p[n++] = (uint8_t)(v | 0x80); v >>= 7; } p[n++] = (uint8_t)v; return n; };
+    size_t w = 0;
+    for (size_t r = 0; r < nrows; ++r) {
+        if (out_off[r + 1] < out_off[r]) return fail(DGX_ERR_ARG, "offsets are not ascending at row %zu", r);
+        const uint64_t n = out_off[r + 1] - out_off[r];
+        const uint64_t payload = n * 8;
+        const uint64_t inner = n ? 1 + varint_len(payload) + payload : 0;  // the row's pb.List message
+        const size_t total = 1 + varint_len(inner) + (size_t)inner;
+        if (buf) {
+            if (w + total > buf_cap) return fail(DGX_ERR_CAP, "uid_matrix does not fit buf_cap (%zu)", buf_cap);
+            if (n && !out) return fail(DGX_ERR_ARG, "null values");
+            uint8_t* p = buf + w;
+            *p++ = 0x0A;
+            p += put_varint(p, inner);
+            if (n) {
+                *p++ = 0x0A;
+                p += put_varint(p, payload);
+                memcpy(p, out + out_off[r], (size_t)payload);
+            }
+        }
+        w += total;
+    }
+    *len = w;
+    return DGX_OK;
+}
+
 extern "C" int dgx_wire_list_decode(const uint8_t* buf, size_t len, uint64_t* out, size_t out_cap, size_t* out_len) {
     if ((!buf && len) || !out_len) return fail(DGX_ERR_ARG, "null argument");
     wire::Reader r{buf, buf + len};

@@ -71,3 +71,17 @@ def ListFromWire(data) -> pb.List:
     if cnt.value:
         _lib.check(lib.dgx_wire_list_decode(vp, n, out.ctypes.data, cnt.value, C.byref(cnt)))
     return pb.List(out)
+
+
+def UidMatrixToWire(out, out_off) -> bytes:
+    """CSR result (values, nrows + 1 offsets) -> the uid_matrix rows of a serialized pb.Result."""
+    lib = _lib.load()
+    vals = np.ascontiguousarray(out, dtype=np.uint64)
+    offs = np.ascontiguousarray(out_off, dtype=np.uint64)
+    nrows = max(int(offs.size) - 1, 0)
+    n = C.c_size_t(0)
+    vp = vals.ctypes.data if vals.size else None
+    _lib.check(lib.dgx_wire_uid_matrix(vp, offs.ctypes.data, nrows, None, 0, C.byref(n)))
+    buf = np.zeros(max(n.value, 1), np.uint8)
+    _lib.check(lib.dgx_wire_uid_matrix(vp, offs.ctypes.data, nrows, buf.ctypes.data, n.value, C.byref(n)))
+    return buf[:n.value].tobytes()

@@ -168,6 +168,14 @@ int dgx_wire_pack_parse(const uint8_t* buf, size_t len,
  * (proto3 omits an empty repeated field).  The message is hdr || values. */
 size_t dgx_wire_list_header(size_t n, uint8_t* hdr);
 
+/* pb.Result{repeated List uid_matrix = 1} (protos/pb.proto:76-78): frame a CSR result -- the
+ * (out, out_off) pair dgx_intersect_batch / dgx_dev_filter_batch produce, nrows + 1 offsets -- as
+ * the uid_matrix rows of a serialized pb.Result: per row tag 0x0A, the row's byte length, then the
+ * pb.List message (empty rows are `0A 00`).  buf == NULL only sizes.  Other pb.Result fields can be
+ * appended by the caller; DGX_ERR_CAP when buf_cap is too small. */
+int dgx_wire_uid_matrix(const uint64_t* out, const uint64_t* out_off, size_t nrows,
+                        uint8_t* buf, size_t buf_cap, size_t* len);
+
 /* Inverse: the uids of a serialized pb.List, packed chunks and unpacked entries in order.
  * out == NULL only counts.  DGX_ERR_CAP when out_cap is too small. */
 int dgx_wire_list_decode(const uint8_t* buf, size_t len, uint64_t* out, size_t out_cap, size_t* out_len);

@@ -33,12 +33,14 @@ def _messages():
     msg("UidPack", [("block_size", 1, F.TYPE_UINT32, False, None), ("blocks", 2, F.TYPE_MESSAGE, True, "UidBlock"),
                     ("alloc_ref", 23, F.TYPE_UINT64, False, None)])
     msg("Posting", [("uid", 1, F.TYPE_FIXED64, False, None), ("value", 2, F.TYPE_BYTES, False, None)])
+    msg("Result", [("uid_matrix", 1, F.TYPE_MESSAGE, True, "List"), ("counts", 3, F.TYPE_UINT32, True, None),
+                    ("intersect_dest", 4, F.TYPE_BOOL, False, None)])
     msg("PostingList", [("pack", 1, F.TYPE_MESSAGE, False, "UidPack"), ("postings", 2, F.TYPE_MESSAGE, True, "Posting"),
                         ("commit_ts", 3, F.TYPE_UINT64, False, None), ("splits", 4, F.TYPE_UINT64, True, None)])
     pool = descriptor_pool.DescriptorPool()
     pool.Add(fdp)
     return {n: message_factory.GetMessageClass(pool.FindMessageTypeByName("pbt." + n))
-            for n in ("List", "UidBlock", "UidPack", "Posting", "PostingList")}
+            for n in ("List", "UidBlock", "UidPack", "Posting", "PostingList", "Result")}
 
 
 M = _messages()
@@ -136,6 +138,26 @@ def test_list_to_wire_matches_protobuf(n):
     back = wire.ListFromWire(want)
     assert np.array_equal(back.Uids, uids)
     assert wire.ListToWire(None) == b""
+
+
+def test_uid_matrix_matches_protobuf():
+    """A CSR batch result framed as pb.Result.uid_matrix (protos/pb.proto:76-78), empty rows included."""
+    rng = np.random.default_rng(3)
+    rows = [np.sort(rng.integers(0, 2**63, int(n), dtype=np.uint64)) for n in (0, 1, 5, 0, 300, 16, 0)]
+    out = np.concatenate(rows)
+    off = np.concatenate([[0], np.cumsum([r.size for r in rows])]).astype(np.uint64)
+    m = M["Result"]()
+    for r in rows:
+        m.uid_matrix.add().uids.extend(int(x) for x in r)
+    assert wire.UidMatrixToWire(out, off) == m.SerializeToString()
+    # the caller appends other fields of pb.Result behind the rows
+    m.intersect_dest = True
+    tail = bytes.fromhex("20 01")
+    assert wire.UidMatrixToWire(out, off) + tail == m.SerializeToString()
+    back = M["Result"]()
+    back.ParseFromString(wire.UidMatrixToWire(out, off))
+    assert [list(l.uids) for l in back.uid_matrix] == [r.tolist() for r in rows]
+    assert wire.UidMatrixToWire(np.zeros(0, np.uint64), np.zeros(1, np.uint64)) == b""
 
 
 def test_list_unpacked_and_split_encodings():
