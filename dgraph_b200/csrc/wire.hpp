@@ -29,6 +29,7 @@ struct Reader {
         for (int shift = 0; shift < 64; shift += 7) {
             if (p >= end) return false;
             const uint8_t b = *p++;
+            if (shift == 63 && b > 1) return false;  // 10th byte: only bit 63 may be set (protowire: overflow)
             r |= (uint64_t)(b & 0x7f) << shift;
             if (!(b & 0x80)) { *v = r; return true; }
         }

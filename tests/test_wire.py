@@ -225,3 +225,74 @@ def test_malformed_list_and_caps():
     view = _lib.PackView()
     off = np.zeros(2, np.uint64)
     assert lib.dgx_wire_pack_parse(raw, len(raw), None, None, off.ctypes.data, None, 0, 0, C.byref(view)) == -4
+
+
+def test_differential_fuzz_against_protobuf_runtime():
+    """Random and mutated byte strings: the parser accepts exactly what the protobuf runtime accepts and reads
+    the same fields.  One documented divergence is excluded: a 10-byte varint whose last byte exceeds 1
+    overflows 64 bits -- Go's protowire (the reference's runtime, google.golang.org/protobuf) and this parser
+    reject it, the Python runtime silently drops the extra bits."""
+    import random
+    import re
+
+    def ours(data):
+        try:
+            p = wire.ParseUidPack(data)
+        except _lib.DgxError:
+            return None
+        return (p.block_size, [(int(p.base[i]), int(p.num_uids[i]),
+                                p.deltas[int(p.delta_off[i]):int(p.delta_off[i + 1])].tobytes()) for i in range(p.nblocks)])
+
+    def runtime(data):
+        m = M["UidPack"]()
+        try:
+            m.ParseFromString(data)
+        except Exception:  # noqa: BLE001  (DecodeError)
+            return None
+        return (m.block_size, [(b.base, b.num_uids, bytes(b.deltas)) for b in m.blocks])
+
+    rng = random.Random(20260921)
+    valid = []
+    for _ in range(40):
+        m = M["UidPack"]()
+        m.block_size = rng.choice([0, 1, 5, 256, 2**32 - 1])
+        for _ in range(rng.randrange(0, 5)):
+            b = m.blocks.add()
+            b.base = rng.choice([0, 1, 2**40, 2**64 - 1])
+            b.num_uids = rng.randrange(0, 300)
+            b.deltas = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 12)))
+        m.alloc_ref = rng.choice([0, 5, 2**63])
+        valid.append(m.SerializeToString())
+    long_varint = re.compile(rb"[\x80-\xff]{9}")
+    checked = accepted = 0
+    for it in range(20000):
+        if it % 3 == 0:
+            data = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 24)))
+        else:
+            d = bytearray(rng.choice(valid))
+            for _ in range(rng.randrange(1, 4)):
+                op = rng.randrange(3)
+                if op == 0 and d:
+                    d[rng.randrange(len(d))] = rng.randrange(256)
+                elif op == 1 and d:
+                    del d[rng.randrange(len(d))]
+                else:
+                    d.insert(rng.randrange(len(d) + 1), rng.randrange(256))
+            data = bytes(d)
+        if long_varint.search(data):
+            continue
+        want = runtime(data)
+        assert ours(data) == want, data.hex()
+        checked += 1
+        accepted += want is not None
+    assert checked > 10000 and accepted > 1000
+
+
+def test_varint_overflow_follows_go_protowire():
+    """protowire.ConsumeVarint: the 10th byte may only carry bit 63."""
+    ok = bytes.fromhex("b8 01 ff ff ff ff ff ff ff ff ff 01")      # alloc_ref = 2^64 - 1
+    assert wire.ParseUidPack(ok).nblocks == 0
+    with pytest.raises(_lib.DgxError):
+        wire.ParseUidPack(bytes.fromhex("b8 01 ff ff ff ff ff ff ff ff ff 02"))
+    with pytest.raises(_lib.DgxError):
+        wire.ParseUidPack(bytes.fromhex("b8 01 80 80 80 80 80 80 80 80 80 80 01"))  # 11 bytes
