@@ -5,13 +5,19 @@ NVFLAGS ?= -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-maybe-un
 CSRC := dgraph_b200/csrc
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/dgx.h
 
+.PHONY: all prof clean
 all: dgraph_b200/libdgx.so oracle/liboracle.so
 
 dgraph_b200/libdgx.so: $(CSRC)/dgx_api.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/dgx_api.cu -lcudart
 
+# instrumented build for tools/prof_pipe_waits.py (per-role wait / phase cycle counters; slower, never benchmarked)
+prof: dgraph_b200/libdgx_prof.so
+dgraph_b200/libdgx_prof.so: $(CSRC)/dgx_api.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -DDGX_PIPE_PROF -shared -o $@ $(CSRC)/dgx_api.cu -lcudart
+
 oracle/liboracle.so: oracle/oracle.c oracle/oracle.h
 	$(MAKE) -C oracle liboracle.so
 
 clean:
-	rm -f dgraph_b200/libdgx.so oracle/liboracle.so
+	rm -f dgraph_b200/libdgx.so dgraph_b200/libdgx_prof.so oracle/liboracle.so

@@ -2,7 +2,7 @@
 """Wait-time breakdown of filter_pipe_kernel's warp roles on the C2 workload.
 
 Needs an experimental build with -DDGX_PIPE_PROF (exports dgx_debug_pprof):
-  nvcc ... -DDGX_PIPE_PROF -shared -o dgraph_b200/libdgx_prof.so dgraph_b200/csrc/dgx_api.cu -lcudart
+  make prof        (nvcc ... -DDGX_PIPE_PROF -shared -o dgraph_b200/libdgx_prof.so ...)
   DGX_LIB=$PWD/dgraph_b200/libdgx_prof.so python tools/prof_pipe_waits.py
 Instrumented builds are slower; the numbers are shares of each role's own time, not a bench value.
 """
