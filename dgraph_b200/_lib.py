@@ -35,6 +35,15 @@ class PackView(C.Structure):
     ]
 
 
+class PackRef(C.Structure):
+    """dgx_pack_ref (include/dgx.h): a pack plus the (key, version) that names it in the HBM cache."""
+    _fields_ = [("pack", C.POINTER(PackView)), ("key", C.c_uint64), ("version", C.c_uint64)]
+
+
+class CacheStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("hits", "misses", "evictions", "bytes", "entries", "max_bytes")]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("calls", "uids_in", "uids_out", "h2d_bytes", "d2h_bytes", "kernel_launches")]
 
@@ -58,6 +67,12 @@ SYMBOLS = {
     "dgx_decode": (_int, [C.POINTER(PackView), _u64, _vp, _sz, _szp]),
     "dgx_decode_intersect_sorted": (_int, [C.POINTER(PackView), _u64, _vp, _vp, _sz, _vp, _sz, _szp]),
     "dgx_intersect_compressed": (_int, [C.POINTER(PackView), _u64, _vp, _sz, _vp, _sz, _szp]),
+    "dgx_intersect_sorted_packed": (_int, [C.POINTER(PackRef), _sz, _vp, _sz, _szp]),
+    "dgx_cache_configure": (_int, [_sz]),
+    "dgx_cache_clear": (None, []),
+    "dgx_cache_get_stats": (None, [C.POINTER(CacheStats)]),
+    "dgx_index_of_batch": (_int, [_vp, _sz, _vp, _sz, _vp]),
+    "dgx_intersect_batch_shared": (_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz]),
     "dgx_lane_create": (_vp, [_int, _vp]),
     "dgx_lane_destroy": (None, [_vp]),
     "dgx_lane_sync": (_int, [_vp]),

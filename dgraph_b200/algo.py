@@ -117,3 +117,58 @@ def IntersectBatch(a: np.ndarray, a_off: np.ndarray, b: np.ndarray, b_off: np.nd
     out_off = np.zeros(npairs + 1, dtype=np.uint64)
     _lib.check(lib.dgx_intersect_batch(_p(a), _p(a_off), _p(b), _p(b_off), npairs, _p(out), _p(out_off), cap))
     return out[: int(out_off[-1])], out_off
+
+
+def IntersectSortedPacked(packs, keys=None) -> List:
+    """algo.IntersectSorted over lists held as UidPacks (dgx_intersect_sorted_packed): the packs cross
+    PCIe compressed and are decoded on the device (codec.Decode(p, 0) for each, codec/codec.go:444).
+
+    keys: optional [(key, version)] naming each pack for the HBM-resident cache (0 = anonymous)."""
+    from .codec import ExactLen, view_of
+
+    if len(packs) == 0:
+        return List(None)
+    lib = _lib.load()
+    k = len(packs)
+    refs = (_lib.PackRef * k)()
+    keep = []
+    cap = None
+    for i, p in enumerate(packs):
+        if p is None or p.nblocks == 0:
+            refs[i].pack = None
+            cap = 0
+        else:
+            p = p.normalized()
+            v = view_of(p)
+            keep.append((p, v))
+            refs[i].pack = C.pointer(v)
+            n = ExactLen(p)
+            cap = n if cap is None else min(cap, n)
+        refs[i].key, refs[i].version = (keys[i] if keys is not None else (0, 0))
+    out = np.empty(max(cap or 0, 1), dtype=np.uint64)
+    n = C.c_size_t(0)
+    _lib.check(lib.dgx_intersect_sorted_packed(refs, k, _p(out), cap or 0, C.byref(n)))
+    return List(out[: n.value])
+
+
+def IndexOfBatch(u: List, uids) -> np.ndarray:
+    """algo.IndexOf(u, uid) for every uid (algo/uidlist.go:546-552): int64 positions, -1 when absent."""
+    lib = _lib.load()
+    uu = np.zeros(0, np.uint64) if u.Uids is None else u.Uids
+    q = _u64(uids)
+    idx = np.empty(max(q.size, 1), dtype=np.int64)
+    _lib.check(lib.dgx_index_of_batch(_p(uu), uu.size, _p(q), q.size, idx.ctypes.data_as(C.c_void_p)))
+    return idx[: q.size]
+
+
+def IntersectBatchShared(a: np.ndarray, a_off: np.ndarray, b: np.ndarray):
+    """Rows a[a_off[i]:a_off[i+1]] each intersected with the one list b (dgx_intersect_batch_shared):
+    the `algo.IntersectWith(l, sg.DestUIDs, l)` loop of query/query.go:1425-1438."""
+    lib = _lib.load()
+    a, b, a_off = _u64(a), _u64(b), _u64(a_off)
+    npairs = a_off.size - 1
+    cap = int(np.minimum(np.diff(a_off.astype(np.int64)), b.size).sum()) if npairs > 0 else 0
+    out = np.empty(max(cap, 1), dtype=np.uint64)
+    out_off = np.zeros(npairs + 1, dtype=np.uint64)
+    _lib.check(lib.dgx_intersect_batch_shared(_p(a), _p(a_off), npairs, _p(b), b.size, _p(out), _p(out_off), cap))
+    return out[: int(out_off[-1])], out_off

@@ -11,9 +11,8 @@
 // window; (2) lane i walks block i's tag bytes (the only serial dependence:
 // group g+1 starts BytesUsed[tag_g] after group g) and records group offsets;
 // (3) all lanes decode a block's groups in parallel -- unaligned 16-byte read,
-// four extractions, warp prefix sum of deltas (32-bit: a block never spans a
-// 32-bit-MSB boundary, codec.go:116-120) -- into a staging row that is written
-// out as coalesced 16-byte stores.
+// four extractions, warp prefix sum of deltas (64-bit, `last + uint64(delta)` as in
+// codec.go:191-196) -- into a staging row that is written out as coalesced 16-byte stores.
 #pragma once
 
 #include "common.cuh"
@@ -140,17 +139,9 @@ struct __align__(128) DWarpSmem {
     u64 mbar;
 };
 
-__global__ void __launch_bounds__(D_NT) decode_kernel(const DPack pk, const DSeek* __restrict__ seekp,
-                                                      u64* __restrict__ out, u64 out_cap) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    DWarpSmem& S = reinterpret_cast<DWarpSmem*>(smem_raw)[wid];
-
-    const u64 first_block = seekp->first_block;
-    const u64 skip = seekp->skip;
-    if (seekp->out_len > out_cap) return;  // error already flagged by decode_seek_kernel
-
-    const u64 gw = (u64)blockIdx.x * D_WARPS + wid;
+// One warp decodes blocks [first_block + gw*D_BPW, +D_BPW) of `pk` into out[uid_off - skip ...].
+__device__ __forceinline__ void decode_warp_run(const DPack& pk, u64 first_block, u64 skip, u64* __restrict__ out,
+                                                u64 gw, DWarpSmem& S, int lane) {
     u64 b = first_block + gw * D_BPW;
     const u64 bend = (b + D_BPW < pk.nblocks) ? b + D_BPW : pk.nblocks;
     if (b >= bend) return;  // whole warp
@@ -224,10 +215,15 @@ __global__ void __launch_bounds__(D_NT) decode_kernel(const DPack pk, const DSee
 
         // ---- (2) tag walk: lane i records the byte offset of every group of block i
         if (lane < nb) {
+            // a corrupt tag may claim more bytes than the block holds: the walk stops at the block's
+            // end (the reference zero-pads a short tail, codec.go:176-188; here the next block's
+            // bytes are read instead -- garbage in, garbage out, but never outside the window)
             u32 off = (u32)(doff - win0);
+            const u32 off_end = (u32)(dnext - win0);
             for (u32 g = 0; g < ngroups; ++g) {
                 S.goff[g * D_TSTRIDE + lane] = (unsigned short)off;
                 off += gv_bytes_used(S.payload[off]);
+                off = off < off_end ? off : off_end;
             }
         }
         __syncwarp();
@@ -240,7 +236,7 @@ __global__ void __launch_bounds__(D_NT) decode_kernel(const DPack pk, const DSee
             const u64 uoff_i = __shfl_sync(0xffffffffu, uoff, i);
             const u32 ng_i = __shfl_sync(0xffffffffu, ngroups, i);
             if (lane == 0) S.stage[0] = base_i;
-            u32 carry = 0;
+            u64 carry = 0;
             for (u32 g0 = 0; g0 < ng_i; g0 += 32) {
                 const u32 g = g0 + lane;
                 u32 d0 = 0, d1 = 0, d2 = 0, d3 = 0;
@@ -265,20 +261,22 @@ __global__ void __launch_bounds__(D_NT) decode_kernel(const DPack pk, const DSee
                     d2 = extract(l0 + l1, l2);
                     d3 = extract(l0 + l1 + l2, l3);
                 }
-                const u32 p1 = d0, p2 = d0 + d1, p3 = p2 + d2, p4 = p3 + d3;
-                u32 inc = p4;
+                // running sums are 64-bit like the reference's `last + uint64(delta)` (codec.go:191-196):
+                // packs produced by the Encoder never carry more than 2^32 per block, hand-built ones may
+                const u64 p1 = d0, p2 = p1 + d1, p3 = p2 + d2, p4 = p3 + d3;
+                u64 inc = p4;
 #pragma unroll
                 for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    u32 t = __shfl_up_sync(0xffffffffu, inc, dlt);
+                    u64 t = __shfl_up_sync(0xffffffffu, inc, dlt);
                     if (lane >= dlt) inc += t;
                 }
-                const u32 ex = carry + inc - p4;
+                const u64 ex = base_i + carry + inc - p4;
                 if (g < ng_i) {
                     const u32 idx = 1u + 4u * g;  // uid index of this group's first value
-                    S.stage[idx] = base_i + (u64)(ex + p1);
-                    S.stage[idx + 1] = base_i + (u64)(ex + p2);
-                    S.stage[idx + 2] = base_i + (u64)(ex + p3);
-                    S.stage[idx + 3] = base_i + (u64)(ex + p4);
+                    S.stage[idx] = ex + p1;
+                    S.stage[idx + 1] = ex + p2;
+                    S.stage[idx + 2] = ex + p3;
+                    S.stage[idx + 3] = ex + p4;
                 }
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
@@ -300,6 +298,38 @@ __global__ void __launch_bounds__(D_NT) decode_kernel(const DPack pk, const DSee
         }
         b += nb;
     }
+}
+
+__global__ void __launch_bounds__(D_NT) decode_kernel(const DPack pk, const DSeek* __restrict__ seekp,
+                                                      u64* __restrict__ out, u64 out_cap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    DWarpSmem& S = reinterpret_cast<DWarpSmem*>(smem_raw)[wid];
+    if (seekp->out_len > out_cap) return;  // error already flagged by decode_seek_kernel
+    decode_warp_run(pk, seekp->first_block, seekp->skip, out, (u64)blockIdx.x * D_WARPS + wid, S, lane);
+}
+
+// Several packs decoded in full (seek 0) by ONE launch: the k posting lists of a query arrive as
+// UidPacks (1.3-1.6 B/UID over PCIe) and are expanded side by side.  Job j owns warps
+// [warp_base[j], warp_base[j+1]) of the grid.
+struct DJob {
+    DPack pk;
+    u64* out;
+    u64 warp_base;
+};
+__global__ void __launch_bounds__(D_NT) decode_batch_kernel(const DJob* __restrict__ jobs, u32 njobs, u64 nwarps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    DWarpSmem& S = reinterpret_cast<DWarpSmem*>(smem_raw)[wid];
+    const u64 gw = (u64)blockIdx.x * D_WARPS + wid;
+    if (gw >= nwarps) return;
+    u32 lo = 0, hi = njobs;  // last job with warp_base <= gw
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (jobs[mid].warp_base <= gw) lo = mid; else hi = mid;
+    }
+    const DPack pk = jobs[lo].pk;
+    decode_warp_run(pk, 0, 0, jobs[lo].out, gw - jobs[lo].warp_base, S, lane);
 }
 
 }  // namespace dgx

@@ -13,16 +13,23 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
+
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "decode_kernel.cuh"
 #include "filter_kernel.cuh"
 #include "filter_pipe.cuh"
 #include "merge_kernel.cuh"
 #include "merge_multi.cuh"
+#include "probe_kernel.cuh"
 #include "wire.hpp"
 
 using namespace dgx;
@@ -75,6 +82,8 @@ constexpr size_t kPipeSmemMax = 220 * 1024;
 // ---------------------------------------------------------------------------
 // arenas
 // ---------------------------------------------------------------------------
+static cudaError_t pinned_alloc(void** p, size_t bytes);  // NUMA-aware cudaMallocHost (below)
+static void numa_probe(int device);
 // Device scratch: bump allocator, reset at the start of every public op (safe:
 // later work on the same stream is ordered after earlier kernels).
 struct DevArena {
@@ -131,7 +140,7 @@ struct HostArena {
         if (chunks.empty() || chunks.back().used + bytes > chunks.back().cap) {
             size_t ncap = std::max(bytes, chunks.empty() ? (size_t(1) << 20) : chunks.back().cap * 2);
             void* p = nullptr;
-            cudaError_t e = cudaMallocHost(&p, ncap);
+            cudaError_t e = pinned_alloc(&p, ncap);
             if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMallocHost(%zu) failed: %s", ncap, cudaGetErrorString(e));
             chunks.push_back({(char*)p, ncap, 0});
         }
@@ -167,8 +176,11 @@ struct dgx_lane {
     int* d_err = nullptr;   // device error flag (out_cap overflow)
     int* h_err = nullptr;   // pinned mirror
     uint64_t* h_word = nullptr;  // pinned scratch for lengths (8 words)
+    uint64_t* h_head = nullptr;  // pinned landing zone for the head of a result (kSpecHead values)
     uint64_t launches = 0;
 };
+// Results up to this many values reach the host in the same round trip as their length.
+constexpr size_t kSpecHead = 8192;
 
 // Start of a device-level op on a lane: bind the device, recycle the workspace.  The pinned descriptor
 // staging is only recycled at a lane sync (queued H2D copies read from it); a caller that queues thousands
@@ -206,11 +218,14 @@ extern "C" int dgx_init(int device) {
         return fail(DGX_ERR_NODEV, "libdgx is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
     CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sizeof(DWarpSmem) * D_WARPS)));
+    CK(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(sizeof(DWarpSmem) * D_WARPS)));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * F_TA * sizeof(u64) + kScapMax)));
     CK(cudaFuncSetAttribute(filter_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
     CK(cudaFuncSetAttribute(mmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * MM_CP * sizeof(u64))));
     g_num_sms = prop.multiProcessorCount;
+    numa_probe(device);
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
     if (const char* s = getenv("DGX_MERGE")) g_merge_multi = (strcmp(s, "tree") != 0);
     if (const char* s = getenv("DGX_MERGE_MULTI_MIN")) g_merge_multi_min = (size_t)atoll(s);
@@ -228,6 +243,7 @@ extern "C" int dgx_init(int device) {
 }
 
 extern "C" void dgx_shutdown(void) {
+    dgx_cache_clear();
     std::lock_guard<std::mutex> lk(g_mu);
     for (dgx_lane* l : g_pool) dgx_lane_destroy(l);
     g_pool.clear();
@@ -244,10 +260,59 @@ extern "C" int dgx_describe(char* buf, size_t n) {
     return DGX_OK;
 }
 
+// Pinned host memory is placed on the NUMA node the GPU hangs off: a DMA from the far socket runs at
+// about half the PCIe rate.  While the pages are allocated the calling thread is moved to the GPU's
+// node (first touch) and, where the container allows it, the memory policy prefers that node; both
+// are restored afterwards and every step is best effort (DGX_NUMA=0 turns it off).
+static int g_numa_node = -2;  // -2 unknown, -1 none
+static cpu_set_t g_numa_cpus;
+static void numa_probe(int device) {
+    g_numa_node = -1;
+    if (const char* s = getenv("DGX_NUMA")) if (atoi(s) == 0) return;
+    char bus[32] = {0}, path[128];
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    CPU_ZERO(&g_numa_cpus);
+    int a, b, n = 0;
+    while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        int c = fgetc(f);
+        if (c == '-') { if (fscanf(f, "%d", &b) != 1) b = a; c = fgetc(f); }
+        for (int i = a; i <= b && i < CPU_SETSIZE; ++i) { CPU_SET(i, &g_numa_cpus); ++n; }
+        if (c != ',') break;
+    }
+    fclose(f);
+    if (n) g_numa_node = node;
+}
+static cudaError_t pinned_alloc(void** p, size_t bytes) {
+    cpu_set_t old;
+    bool moved = false, policy = false;
+    if (g_numa_node >= 0) {
+        if (sched_getaffinity(0, sizeof(old), &old) == 0 && sched_setaffinity(0, sizeof(g_numa_cpus), &g_numa_cpus) == 0) moved = true;
+        unsigned long mask[16] = {0};
+        if (g_numa_node < 1024) {
+            mask[g_numa_node / (8 * sizeof(unsigned long))] |= 1ul << (g_numa_node % (8 * sizeof(unsigned long)));
+            policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024ul) == 0;
+        }
+    }
+    const cudaError_t e = cudaMallocHost(p, bytes ? bytes : 1);
+    if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    if (moved) sched_setaffinity(0, sizeof(old), &old);
+    return e;
+}
+
 extern "C" void* dgx_host_alloc(size_t bytes) {
     if (dgx_init(-1) != DGX_OK) return nullptr;
     void* p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    if (pinned_alloc(&p, bytes) != cudaSuccess) return nullptr;
     return p;
 }
 extern "C" void dgx_host_free(void* p) {
@@ -266,6 +331,12 @@ extern "C" void dgx_get_stats(dgx_stats* out) {
 extern "C" dgx_lane* dgx_lane_create(int device, void* stream) {
     if (dgx_init(device) != DGX_OK) return nullptr;
     if (device < 0) device = g_device;
+    // One device per process (one alpha process per GPU): kernel attributes, the SM count and the
+    // host-pointer entry points are bound to the device dgx_init chose.
+    if (device != g_device) {
+        fail(DGX_ERR_ARG, "libdgx is bound to device %d in this process; lane requested on device %d", g_device, device);
+        return nullptr;
+    }
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
     dgx_lane* l = new dgx_lane();
     l->device = device;
@@ -275,12 +346,14 @@ extern "C" dgx_lane* dgx_lane_create(int device, void* stream) {
         if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; return nullptr; }
         l->own_stream = true;
     }
-    if (cudaMalloc(&l->d_err, 256) != cudaSuccess || cudaMallocHost(&l->h_err, 256) != cudaSuccess) {
+    if (cudaMalloc(&l->d_err, 256) != cudaSuccess ||
+        pinned_alloc((void**)&l->h_err, 4096 + kSpecHead * sizeof(uint64_t)) != cudaSuccess) {
         fail(DGX_ERR_OOM, "lane allocation failed");
         delete l;
         return nullptr;
     }
     l->h_word = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(l->h_err) + 64);
+    l->h_head = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(l->h_err) + 4096);
     *l->h_err = 0;
     cudaMemsetAsync(l->d_err, 0, 256, l->stream);
     return l;
@@ -746,7 +819,11 @@ static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_
     int rc;
     if (!d_mem) {
         if (arena) { rc = arena->alloc(total, &d_mem); if (rc) return rc; }
-        else { cudaError_t e = cudaMalloc(&d_mem, total); if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e)); }
+        else {
+            cudaError_t e = cudaMalloc(&d_mem, total);
+            if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+            out->d_mem = d_mem;  // owned by *out from here on, also when a later step fails
+        }
     }
     // uid_off (exclusive prefix of NumUids) and max NumUids: layout metadata, computed while flattening
     void* h_raw;
@@ -757,8 +834,17 @@ static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_
     uint32_t max_num = 0;
     for (size_t i = 0; i < nb; ++i) {
         h_uoff[i] = acc;
-        acc += v->num_uids[i];
-        max_num = std::max(max_num, v->num_uids[i]);
+        const uint32_t num = v->num_uids[i];
+        acc += num;
+        max_num = std::max(max_num, num);
+        // The kernels trust the block table: offsets must ascend and every block must hold at least
+        // the 5-byte minimum of each group its NumUids needs (ceil((n-1)/4), codec.go:76-96).  A pack
+        // that fails this is refused (the shim stays on the Go path) instead of being walked.
+        const uint64_t b0 = v->delta_off[i], b1 = v->delta_off[i + 1];
+        const uint64_t need = num > 1 ? 5ull * ((uint64_t)(num + 2) / 4) : 0;
+        if (b1 < b0 || b1 - b0 < need)
+            return fail(DGX_ERR_ARG, "malformed UidPack: block %zu has %lld delta bytes, NumUids %u needs >= %llu",
+                        i, (long long)(b1 - b0), num, (unsigned long long)need);
     }
     h_uoff[nb] = acc;
     char* d = (char*)d_mem;
@@ -790,9 +876,9 @@ extern "C" int dgx_dev_pack_upload(dgx_lane* l, const dgx_pack_view* v, dgx_dev_
     CK(cudaSetDevice(l->device));
     dgx_dev_pack* pk = new dgx_dev_pack();
     int rc = pack_upload_impl(l, v, nullptr, nullptr, pk);
-    if (rc) { delete pk; return rc; }
     // the pinned uid_off staging must outlive the async copy
-    CK(cudaStreamSynchronize(l->stream));
+    if (rc == DGX_OK && cudaStreamSynchronize(l->stream) != cudaSuccess) rc = fail(DGX_ERR_CUDA, "pack upload failed");
+    if (rc) { dgx_dev_pack_free(pk); return rc; }
     *out = pk;
     return DGX_OK;
 }
@@ -869,19 +955,24 @@ static int upload_list(dgx_lane* l, const uint64_t* h, size_t n, uint64_t** d) {
     return DGX_OK;
 }
 
-// sync, read the result length at d_len, copy `len` values to the host
-static int finish_to_host(dgx_lane* l, const uint64_t* d_len, const uint64_t* d_out, uint64_t* out, size_t out_cap,
-                          size_t* out_len) {
+// Result to the host in ONE round trip when it is short: the length word and the first kSpecHead
+// values (fewer if the device buffer is smaller) are copied speculatively before the sync; only a
+// longer result pays a second copy for its tail.  d_cap = values allocated behind d_out.
+static int finish_to_host(dgx_lane* l, const uint64_t* d_len, const uint64_t* d_out, size_t d_cap, uint64_t* out,
+                          size_t out_cap, size_t* out_len) {
+    const size_t head = std::min(std::min(d_cap, out_cap), kSpecHead);
     CK(cudaMemcpyAsync(l->h_word, d_len, sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    if (head) CK(cudaMemcpyAsync(l->h_head, d_out, head * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
     int rc = dgx_lane_sync(l);
     if (rc) return rc;
     const uint64_t n = l->h_word[0];
     if (n > out_cap) return fail(DGX_ERR_CAP, "result (%llu) does not fit out_cap (%zu)", (unsigned long long)n, out_cap);
-    if (n) {
-        CK(cudaMemcpyAsync(out, d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    if (n) memcpy(out, l->h_head, std::min<size_t>(n, head) * sizeof(uint64_t));
+    if (n > head) {
+        CK(cudaMemcpyAsync(out + head, d_out + head, (n - head) * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
         CK(cudaStreamSynchronize(l->stream));
     }
-    g_stats.d2h += n * sizeof(uint64_t) + 8;
+    g_stats.d2h += std::max<uint64_t>(n, head) * sizeof(uint64_t) + 8;
     g_stats.uids_out += n;
     if (out_len) *out_len = (size_t)n;
     return DGX_OK;
@@ -911,7 +1002,7 @@ static int filter_host(int op, const uint64_t* const* lists, const size_t* lens,
     const size_t k_off[2] = {0, k};
     rc = filter_batch_impl(l, op, ld.data(), k_off, 1, (uint64_t*)d_out, cap, (uint64_t*)d_off);
     if (rc) return rc;
-    return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, out, out_cap, out_len);
+    return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, cap, out, out_cap, out_len);
 }
 
 extern "C" int dgx_intersect2(const uint64_t* u, size_t n, const uint64_t* v, size_t m, uint64_t* out,
@@ -960,7 +1051,7 @@ extern "C" int dgx_merge_sorted(const uint64_t* const* lists, const size_t* lens
     if (rc) return rc;
     rc = merge_sorted_impl(l, ld.data(), k, (uint64_t*)d_out, total, (uint64_t*)d_len);
     if (rc) return rc;
-    return finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, out, out_cap, out_len);
+    return finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, total, out, out_cap, out_len);
 }
 
 extern "C" int dgx_intersect_batch(const uint64_t* a, const uint64_t* a_off, const uint64_t* b,
@@ -1029,7 +1120,7 @@ extern "C" int dgx_decode(const dgx_pack_view* p, uint64_t seek, uint64_t* out, 
     if (rc) return rc;
     rc = decode_impl(l, pk.pk, seek, (uint64_t*)d_out, pk.exact_len, (uint64_t*)d_len);
     if (rc) return rc;
-    return finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, out, out_cap, out_len);
+    return finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, pk.exact_len, out, out_cap, out_len);
 }
 
 extern "C" int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek, const uint64_t* const* lists,
@@ -1078,7 +1169,7 @@ extern "C" int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek
     const size_t k_off[2] = {0, k + 1};
     rc = filter_batch_impl(l, DGX_OP_INTERSECT, ld.data(), k_off, 1, (uint64_t*)d_out, cap, (uint64_t*)d_off);
     if (rc) return rc;
-    return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, out, out_cap, out_len);
+    return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, cap, out, out_cap, out_len);
 }
 
 extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
@@ -1090,6 +1181,308 @@ extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_u
     const uint64_t* lists[1] = {v};
     const size_t lens[1] = {m};
     return dgx_decode_intersect_sorted(p, after_uid, lists, lens, 1, out, out_cap, out_len);
+}
+
+// ---------------------------------------------------------------------------
+// HBM-resident pack cache + IntersectSorted over packs
+// ---------------------------------------------------------------------------
+// Production holds posting lists as UidPacks (posting.List.plist.Pack, posting/list.go:1795-1800) and
+// decodes them per query.  Here a pack crosses PCIe compressed (about 1.5 B/UID instead of 8) and is
+// expanded on the device; a pack the caller names with (key, version) -- immutable bytes, e.g. the hash
+// of its Badger key and the commit timestamp of the layer -- stays in HBM in its compressed form and
+// later calls skip the copy.  Eviction is LRU by bytes; entries in use by a running call are pinned.
+static size_t pack_device_bytes(const dgx_pack_view* v) {
+    const size_t nb = v ? v->nblocks : 0;
+    const size_t dbytes = nb ? (size_t)v->delta_off[nb] : 0;
+    const size_t o_del = (nb * 8 + (nb + 1) * 16 + nb * 4 + 15) & ~size_t(15);
+    return o_del + ((dbytes + 15) & ~size_t(15)) + 48;
+}
+
+struct CacheKey {
+    uint64_t key, version;
+    bool operator==(const CacheKey& o) const { return key == o.key && version == o.version; }
+};
+struct CacheKeyHash {
+    size_t operator()(const CacheKey& k) const {
+        uint64_t h = k.key * 0x9E3779B97F4A7C15ull ^ (k.version + 0x7F4A7C15ull + (k.key << 6) + (k.key >> 2));
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+struct CacheEntry {
+    CacheKey id;
+    dgx_dev_pack pk;
+    cudaEvent_t ready = nullptr;  // recorded after the upload: other streams wait on it before reading
+    int refs = 0;
+    std::list<CacheEntry*>::iterator lru;
+};
+static std::mutex g_cache_mu;
+static std::unordered_map<CacheKey, CacheEntry*, CacheKeyHash> g_cache;
+static std::list<CacheEntry*> g_cache_lru;  // front = most recently used
+static size_t g_cache_bytes = 0;
+static size_t g_cache_max = size_t(32) << 30;  // DGX_CACHE_BYTES / dgx_cache_configure
+static bool g_cache_env_read = false;
+static dgx_cache_stats g_cache_stats = {0, 0, 0, 0, 0, 0};
+
+static void cache_free_entry(CacheEntry* e) {
+    // refs == 0: every call that used the entry has synchronised its stream, nothing queued reads it
+    if (e->pk.d_mem) cudaFree(e->pk.d_mem);
+    if (e->ready) cudaEventDestroy(e->ready);
+    g_cache_bytes -= e->pk.bytes;
+    delete e;
+}
+// g_cache_mu held.  Drops least-recently-used idle entries until `extra` more bytes fit.
+static void cache_make_room(size_t extra) {
+    auto it = g_cache_lru.end();
+    while (g_cache_bytes + extra > g_cache_max && it != g_cache_lru.begin()) {
+        --it;
+        CacheEntry* e = *it;
+        if (e->refs > 0) continue;
+        it = g_cache_lru.erase(it);
+        g_cache.erase(e->id);
+        cache_free_entry(e);
+        g_cache_stats.evictions += 1;
+    }
+}
+
+extern "C" int dgx_cache_configure(size_t max_bytes) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_env_read = true;
+    g_cache_max = max_bytes;
+    cache_make_room(0);
+    return DGX_OK;
+}
+extern "C" void dgx_cache_clear(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    const size_t keep = g_cache_max;
+    g_cache_max = 0;
+    cache_make_room(0);
+    g_cache_max = keep;
+}
+extern "C" void dgx_cache_get_stats(dgx_cache_stats* out) {
+    if (!out) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    *out = g_cache_stats;
+    out->bytes = g_cache_bytes;
+    out->entries = g_cache.size();
+    out->max_bytes = g_cache_max;
+}
+
+// A pack made available to lane `l`: from the cache (entry != nullptr, one reference held) or copied
+// into the lane's workspace for this call only.
+struct PackLease {
+    dgx_dev_pack pk;
+    CacheEntry* entry = nullptr;
+};
+static void pack_release(PackLease& pl) {
+    if (!pl.entry) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    pl.entry->refs -= 1;
+    pl.entry = nullptr;
+}
+static int pack_acquire(dgx_lane* l, const dgx_pack_ref& ref, PackLease* out) {
+    const dgx_pack_view* v = ref.pack;
+    if (ref.key != 0) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (!g_cache_env_read) {
+            g_cache_env_read = true;
+            if (const char* s = getenv("DGX_CACHE_BYTES")) g_cache_max = (size_t)strtoull(s, nullptr, 10);
+        }
+        const CacheKey id{ref.key, ref.version};
+        auto it = g_cache.find(id);
+        if (it != g_cache.end()) {
+            CacheEntry* e = it->second;
+            e->refs += 1;
+            g_cache_lru.erase(e->lru);
+            g_cache_lru.push_front(e);
+            e->lru = g_cache_lru.begin();
+            g_cache_stats.hits += 1;
+            CK(cudaStreamWaitEvent(l->stream, e->ready, 0));
+            out->pk = e->pk;
+            out->entry = e;
+            return DGX_OK;
+        }
+        g_cache_stats.misses += 1;
+        const size_t bytes = pack_device_bytes(v);
+        if (v && bytes <= g_cache_max) {
+            cache_make_room(bytes);
+            if (g_cache_bytes + bytes <= g_cache_max) {
+                CacheEntry* e = new CacheEntry();
+                e->id = id;
+                // the enqueue (a handful of async copies) happens under the lock so that a second caller
+                // asking for the same pack finds the recorded event, never a half-built entry
+                int rc = pack_upload_impl(l, v, nullptr, nullptr, &e->pk);
+                if (rc == DGX_OK && (cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming) != cudaSuccess ||
+                                     cudaEventRecord(e->ready, l->stream) != cudaSuccess))
+                    rc = fail(DGX_ERR_CUDA, "cache event failed");
+                if (rc) {
+                    if (e->pk.d_mem) cudaFree(e->pk.d_mem);
+                    if (e->ready) cudaEventDestroy(e->ready);
+                    delete e;
+                    return rc;
+                }
+                e->refs = 1;
+                g_cache_bytes += e->pk.bytes;
+                g_cache_lru.push_front(e);
+                e->lru = g_cache_lru.begin();
+                g_cache.emplace(id, e);
+                out->pk = e->pk;
+                out->entry = e;
+                return DGX_OK;
+            }
+        }
+        // does not fit (cache disabled, pack larger than the cache, everything pinned): one-shot copy
+    }
+    return pack_upload_impl(l, v, nullptr, &l->ws, &out->pk);
+}
+
+// Decode every pack of `pls` in full, side by side, with one launch; d_lists[i] receives pack i.
+static int decode_batch_impl(dgx_lane* l, const PackLease* pls, size_t k, uint64_t** d_lists) {
+    void *h_raw, *d_raw;
+    int rc = l->host.alloc(k * sizeof(DJob), &h_raw);
+    if (rc) return rc;
+    rc = l->ws.alloc(k * sizeof(DJob), &d_raw);
+    if (rc) return rc;
+    DJob* hj = (DJob*)h_raw;
+    u64 warps = 0;
+    u32 nj = 0;
+    for (size_t i = 0; i < k; ++i) {
+        void* d;
+        rc = l->ws.alloc((pls[i].pk.exact_len + 2) * sizeof(uint64_t), &d);
+        if (rc) return rc;
+        d_lists[i] = (uint64_t*)d;
+        if (pls[i].pk.pk.nblocks == 0) continue;
+        hj[nj].pk = pls[i].pk.pk;
+        hj[nj].out = (u64*)d;
+        hj[nj].warp_base = warps;
+        warps += (pls[i].pk.pk.nblocks + D_BPW - 1) / D_BPW;
+        ++nj;
+        g_stats.uids_in += pls[i].pk.exact_len;
+    }
+    if (nj == 0) return DGX_OK;
+    CK(cudaMemcpyAsync(d_raw, h_raw, nj * sizeof(DJob), cudaMemcpyHostToDevice, l->stream));
+    const u64 ctas = (warps + D_WARPS - 1) / D_WARPS;
+    if (ctas > 0x7fffffffull) return fail(DGX_ERR_ARG, "packs too large for one decode launch");
+    decode_batch_kernel<<<(unsigned)ctas, D_NT, sizeof(DWarpSmem) * D_WARPS, l->stream>>>((const DJob*)d_raw, nj, warps);
+    CK(cudaGetLastError());
+    l->launches += 1;
+    g_stats.launches += 1;
+    return DGX_OK;
+}
+
+extern "C" int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k, uint64_t* out, size_t out_cap,
+                                           size_t* out_len) {
+    if (out_len) *out_len = 0;
+    if (k == 0) return DGX_OK;  // IntersectSorted of no lists (algo/uidlist.go:298-300)
+    if (!refs) return fail(DGX_ERR_ARG, "null refs");
+    for (size_t i = 0; i < k; ++i)  // a nil / empty pack decodes to the empty list: the intersection is empty
+        if (!refs[i].pack || refs[i].pack->nblocks == 0) return DGX_OK;
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    std::vector<PackLease> pls(k);
+    std::vector<uint64_t*> d_lists(k, nullptr);
+    int rc = DGX_OK;
+    size_t got = 0;
+    for (; got < k && rc == DGX_OK; ++got) rc = pack_acquire(l, refs[got], &pls[got]);
+    if (rc == DGX_OK) rc = decode_batch_impl(l, pls.data(), k, d_lists.data());
+    size_t cap = SIZE_MAX;
+    void *d_out = nullptr, *d_off = nullptr;
+    if (rc == DGX_OK) {
+        std::vector<ListDesc> ld(k);
+        for (size_t i = 0; i < k; ++i) {
+            ld[i] = {d_lists[i], pls[i].pk.exact_len, nullptr};
+            cap = std::min(cap, pls[i].pk.exact_len);
+        }
+        rc = l->ws.alloc((cap + 2) * sizeof(uint64_t), &d_out);
+        if (rc == DGX_OK) rc = l->ws.alloc(2 * sizeof(uint64_t), &d_off);
+        const size_t k_off[2] = {0, k};
+        if (rc == DGX_OK) rc = filter_batch_impl(l, DGX_OP_INTERSECT, ld.data(), k_off, 1, (uint64_t*)d_out, cap, (uint64_t*)d_off);
+    }
+    if (rc == DGX_OK) rc = finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, cap, out, out_cap, out_len);
+    else cudaStreamSynchronize(l->stream);  // nothing queued may outlive the references released below
+    for (size_t i = 0; i < got; ++i) pack_release(pls[i]);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// IndexOf batch, shared-list batch
+// ---------------------------------------------------------------------------
+extern "C" int dgx_index_of_batch(const uint64_t* u, size_t n, const uint64_t* uids, size_t m, int64_t* idx) {
+    if (m == 0) return DGX_OK;
+    if (!uids || !idx || (n && !u)) return fail(DGX_ERR_ARG, "null argument");
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    uint64_t *d_u, *d_q;
+    void* d_idx;
+    int rc = upload_list(l, u, n, &d_u);
+    if (rc) return rc;
+    rc = upload_list(l, uids, m, &d_q);
+    if (rc) return rc;
+    rc = l->ws.alloc(m * sizeof(int64_t), &d_idx);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)g_num_sms * 16);
+    index_of_kernel<<<blocks, 256, 0, l->stream>>>((const u64*)d_u, (u64)n, (const u64*)d_q, (u64)m, (long long*)d_idx);
+    CK(cudaGetLastError());
+    l->launches += 1;
+    g_stats.launches += 1;
+    g_stats.uids_in += n + m;
+    CK(cudaMemcpyAsync(idx, d_idx, m * sizeof(int64_t), cudaMemcpyDeviceToHost, l->stream));
+    g_stats.d2h += m * sizeof(int64_t);
+    return dgx_lane_sync(l);
+}
+
+static int batch_to_host(dgx_lane* l, const void* d_out, const void* d_off, size_t npairs, uint64_t* out,
+                         uint64_t* out_off, size_t out_cap) {
+    CK(cudaMemcpyAsync(out_off, d_off, (npairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    int rc = dgx_lane_sync(l);
+    if (rc) return rc;
+    const uint64_t n = out_off[npairs];
+    if (n > out_cap) return fail(DGX_ERR_CAP, "batch result (%llu) does not fit out_cap (%zu)", (unsigned long long)n, out_cap);
+    if (n) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+        CK(cudaStreamSynchronize(l->stream));
+    }
+    g_stats.d2h += (n + npairs + 1) * sizeof(uint64_t);
+    g_stats.uids_out += n;
+    return DGX_OK;
+}
+
+extern "C" int dgx_intersect_batch_shared(const uint64_t* a, const uint64_t* a_off, size_t npairs, const uint64_t* b,
+                                          size_t m, uint64_t* out, uint64_t* out_off, size_t out_cap) {
+    if (npairs == 0) { if (out_off) out_off[0] = 0; return DGX_OK; }
+    if (!a_off || !out_off) return fail(DGX_ERR_ARG, "null argument");
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    const size_t na = a_off[npairs] - a_off[0];
+    uint64_t *d_a, *d_b;
+    int rc = upload_list(l, a + a_off[0], na, &d_a);
+    if (rc) return rc;
+    rc = upload_list(l, b, m, &d_b);  // the shared list crosses PCIe once
+    if (rc) return rc;
+    std::vector<ListDesc> ld(2 * npairs);
+    std::vector<size_t> k_off(npairs + 1);
+    size_t cap = 0;
+    for (size_t i = 0; i < npairs; ++i) {
+        const size_t la = a_off[i + 1] - a_off[i];
+        ld[2 * i] = {d_a + (a_off[i] - a_off[0]), la, nullptr};
+        ld[2 * i + 1] = {d_b, m, nullptr};
+        k_off[i] = 2 * i;
+        cap += std::min(la, m);
+    }
+    k_off[npairs] = 2 * npairs;
+    void *d_out, *d_off;
+    rc = l->ws.alloc((cap + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc((npairs + 1) * sizeof(uint64_t), &d_off);
+    if (rc) return rc;
+    rc = filter_batch_impl(l, DGX_OP_INTERSECT, ld.data(), k_off.data(), npairs, (uint64_t*)d_out, cap, (uint64_t*)d_off);
+    if (rc) return rc;
+    return batch_to_host(l, d_out, d_off, npairs, out, out_off, out_cap);
 }
 
 // ---------------------------------------------------------------------------

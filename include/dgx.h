@@ -136,6 +136,49 @@ int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek,
 int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
                              uint64_t* out, size_t out_cap, size_t* out_len);
 
+/* ---- posting lists as production holds them: UidPacks, optionally HBM-resident ----------- */
+/* posting.List keeps its uids as a pb.UidPack (posting/list.go:1795-1800, 1861) and every query
+ * decodes what it needs.  A pack crosses PCIe at ~1.5 B/UID where the decoded list costs 8, so the
+ * entry points below take packs, expand them on the device and run the set operation there.
+ * A pack the caller can NAME stays resident in HBM (compressed) between calls:
+ *   key     != 0: identity of the posting list, e.g. a 64-bit hash of its Badger key; 0 = anonymous
+ *   version     : commit timestamp of the immutable layer the pack was built from (List.minTs);
+ *                 (key, version) must name immutable bytes -- a rollup produces a new version.
+ * On a hit nothing is copied; on a miss the pack is uploaded and kept, least-recently-used packs
+ * making room (capacity: DGX_CACHE_BYTES, default 32 GiB, or dgx_cache_configure). */
+typedef struct dgx_pack_ref {
+    const dgx_pack_view* pack;
+    uint64_t key;
+    uint64_t version;
+} dgx_pack_ref;
+
+/* algo.IntersectSorted over lists held as packs: codec.Decode(pack_i, 0) for every i
+ * (codec/codec.go:444-452) then algo.IntersectSorted (algo/uidlist.go:297-329), the decoded lists
+ * never leaving the device.  A NULL / empty pack is the empty list.  out_cap >= min_i ExactLen. */
+int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k,
+                                uint64_t* out, size_t out_cap, size_t* out_len);
+
+typedef struct dgx_cache_stats {
+    uint64_t hits, misses, evictions;
+    uint64_t bytes, entries, max_bytes;
+} dgx_cache_stats;
+int dgx_cache_configure(size_t max_bytes); /* 0 disables caching (and empties the cache) */
+void dgx_cache_clear(void);
+void dgx_cache_get_stats(dgx_cache_stats* out);
+
+/* algo.IndexOf(u, uid) for a batch of uids (algo/uidlist.go:546-552): idx[i] = position of uids[i]
+ * in the ascending list u, -1 when absent.  `uids` need not be sorted.  Callers: updateDestUids,
+ * updateFacetMatrix, updateUidMatrix (query/query.go:1396-1438, 2594-2608) probe sg.DestUIDs with
+ * every uid of the uid matrix. */
+int dgx_index_of_batch(const uint64_t* u, size_t n, const uint64_t* uids, size_t m, int64_t* idx);
+
+/* dgx_intersect_batch with ONE list `b` shared by every row: out row i = a[a_off[i]..a_off[i+1]) ∩ b.
+ * The `algo.IntersectWith(l, sg.DestUIDs, l)` loop over a uid matrix (query/query.go:1425-1438) and
+ * the per-row filters of worker/task.go:1351, 1616, 1691, 1777; `b` crosses PCIe once. */
+int dgx_intersect_batch_shared(const uint64_t* a, const uint64_t* a_off, size_t npairs,
+                               const uint64_t* b, size_t m,
+                               uint64_t* out, uint64_t* out_off, size_t out_cap);
+
 /* ---- protobuf wire-format adjacency (host only, no device needed) ----------- */
 /* Posting lists reach the path as serialized pb.PostingList values read from Badger
  * (proto.Unmarshal, posting/list.go:1045, posting/mvcc.go:634) and leave it as pb.List

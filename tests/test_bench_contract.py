@@ -34,9 +34,22 @@ def test_reference_arm_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert cb["cores"] == min(2, os.cpu_count())  # the threads that are actually busy: one per query
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_same_config_at_n_gpus():
+    """At N GPUs the reference arm runs the whole job's N x Q queries on rank 0 and reports the GPU arm's config."""
+    r = run("--impl", "reference", "--gpus", "2", "--queries", "2", "--steps", "1", "--warmup", "1",
+            env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["n_gpus"] == 2 and d["config"]["queries_per_gpu"] == 2
+    assert "2 GPU(s)" in d["config"]["parallelism"]
+    assert d["cpu_baseline"]["cores"] == min(4, os.cpu_count())
+    assert "4 queries (2 x 2)" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -1,0 +1,287 @@
+"""GPU parity, round-2 entry points and BASELINE-size configs: libdgx (through the C ABI) vs the CPU
+oracle, bit-exact.  Runs on a B200 only (`pytest -m gpu`).
+
+ - IntersectSorted over packs (dgx_intersect_sorted_packed) with and without the HBM pack cache
+ - IndexOf batch, shared-list batch
+ - malformed packs are refused, not walked
+ - BASELINE configs[2] (1e8-UID pack -> decode -> IntersectSorted), configs[3] (10k pairs, power-law sizes),
+   configs[4] (MergeSorted k=64 sum 1e8 + Difference) at full size: order-sensitive 64-bit hash + length +
+   sampled positions against the oracle (full compare up to 1e7 outputs, hash above).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import gen  # noqa: E402
+from test_gpu_parity import L, eq, to_pack  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dgx():
+    import dgraph_b200
+    from dgraph_b200 import _lib
+
+    lib = _lib.load()
+    _lib.check(lib.dgx_init(-1))
+    return dgraph_b200
+
+
+def order_hash(a: np.ndarray) -> int:
+    """64-bit order-sensitive hash: sum_i (a[i] * M1 + i * M2) ^ rot, wrapping (numpy uint64 arithmetic)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    i = np.arange(a.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = a * np.uint64(0x9E3779B97F4A7C15) + i * np.uint64(0xC2B2AE3D27D4EB4F)
+        x ^= x >> np.uint64(29)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        return int(x.sum(dtype=np.uint64))
+
+
+def same(got, want, what):
+    """Full compare up to 1e7 values, hash + length + 1e6 sampled positions above."""
+    got = np.asarray(got, dtype=np.uint64)
+    want = np.asarray(want, dtype=np.uint64)
+    assert got.size == want.size, f"{what}: len got {got.size} want {want.size}"
+    if got.size <= 10_000_000:
+        eq(got, want, what)
+        return
+    assert order_hash(got) == order_hash(want), f"{what}: order-sensitive hash differs"
+    pos = np.random.default_rng(5).integers(0, got.size, 1_000_000)
+    assert np.array_equal(got[pos], want[pos]), f"{what}: sampled positions differ"
+
+
+# ---- IntersectSorted over packs, pack cache -------------------------------------------------------
+
+def test_intersect_sorted_packed(dgx, orc):
+    rng = np.random.default_rng(31)
+    master = gen.zipf_gaps(rng, 400_000)
+    for k, p, bs in ((1, 0.5, 256), (2, 0.5, 256), (3, 0.3, 10), (8, 0.25, 256), (8, 0.9, 256), (12, 0.8, 64)):
+        lists = [gen.thin(rng, master, p) for _ in range(k)]
+        packs = [to_pack(dgx, orc.encode(l, bs)) for l in lists]
+        got = dgx.algo.IntersectSortedPacked(packs)
+        eq(got.Uids, orc.intersect_sorted(lists), f"packed k={k} p={p} bs={bs}")
+    # nil / empty packs: the empty list; no packs: &pb.List{}
+    lists = [gen.thin(rng, master, 0.5) for _ in range(3)]
+    packs = [to_pack(dgx, orc.encode(l, 256)) for l in lists]
+    assert dgx.algo.IntersectSortedPacked(packs[:2] + [None]).tolist() == []
+    assert dgx.algo.IntersectSortedPacked([]).Uids is None
+    # values across 32-bit-MSB block splits and at the top of the range
+    hi = np.sort(rng.integers(2**63, 2**64 - 1, 50_000, dtype=np.uint64))
+    hi = np.unique(hi)
+    a, b = hi[rng.random(hi.size) < 0.7], hi[rng.random(hi.size) < 0.7]
+    got = dgx.algo.IntersectSortedPacked([to_pack(dgx, orc.encode(a, 256)), to_pack(dgx, orc.encode(b, 256))])
+    eq(got.Uids, orc.intersect_sorted([a, b]), "packed full-range")
+
+
+def test_pack_cache(dgx, orc):
+    from dgraph_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(32)
+    master = gen.zipf_gaps(rng, 300_000)
+    lists = [gen.thin(rng, master, 0.5) for _ in range(4)]
+    packs = [to_pack(dgx, orc.encode(l, 256)) for l in lists]
+    want = orc.intersect_sorted(lists)
+    lib.dgx_cache_clear()
+    _lib.check(lib.dgx_cache_configure(1 << 30))
+    st = _lib.CacheStats()
+    lib.dgx_cache_get_stats(C.byref(st))
+    h0, m0 = st.hits, st.misses
+    keys = [(1000 + i, 7) for i in range(4)]
+    h2d0 = _lib.stats()["h2d_bytes"]
+    eq(dgx.algo.IntersectSortedPacked(packs, keys).Uids, want, "cache cold")
+    h2d1 = _lib.stats()["h2d_bytes"]
+    eq(dgx.algo.IntersectSortedPacked(packs, keys).Uids, want, "cache warm")
+    h2d2 = _lib.stats()["h2d_bytes"]
+    lib.dgx_cache_get_stats(C.byref(st))
+    assert st.misses - m0 == 4 and st.hits - h0 == 4 and st.entries >= 4
+    assert h2d1 - h2d0 > sum(p.deltas.size for p in packs)      # the cold call copied the packs
+    assert h2d2 - h2d1 < 64 * 1024                               # the warm call copied descriptors only
+    # a new version of a key names different bytes: it must not hit the old entry
+    lists2 = [gen.thin(rng, master, 0.4) for _ in range(4)]
+    packs2 = [to_pack(dgx, orc.encode(l, 256)) for l in lists2]
+    eq(dgx.algo.IntersectSortedPacked(packs2, [(1000 + i, 8) for i in range(4)]).Uids, orc.intersect_sorted(lists2), "new version")
+    # eviction: a cache that holds about two packs still answers correctly and stays within its budget
+    one = lib.dgx_cache_get_stats
+    _lib.check(lib.dgx_cache_configure(int(2.5 * packs[0].deltas.size)))
+    for rep in range(3):
+        eq(dgx.algo.IntersectSortedPacked(packs, [(2000 + i, 1) for i in range(4)]).Uids, want, f"evicting rep {rep}")
+    one(C.byref(st))
+    assert st.bytes <= st.max_bytes and st.evictions > 0
+    # disabled cache: named packs still work (one-shot copies)
+    _lib.check(lib.dgx_cache_configure(0))
+    eq(dgx.algo.IntersectSortedPacked(packs, keys).Uids, want, "cache disabled")
+    one(C.byref(st))
+    assert st.entries == 0
+    _lib.check(lib.dgx_cache_configure(32 << 30))
+
+
+def test_pack_cache_concurrent(dgx, orc):
+    import threading
+
+    rng = np.random.default_rng(33)
+    master = gen.zipf_gaps(rng, 200_000)
+    lists = [gen.thin(rng, master, 0.5) for _ in range(6)]
+    packs = [to_pack(dgx, orc.encode(l, 256)) for l in lists]
+    errs = []
+
+    def work(t):
+        try:
+            r = np.random.default_rng(t)
+            for _ in range(8):
+                sel = sorted(r.choice(6, 3, replace=False).tolist())
+                got = dgx.algo.IntersectSortedPacked([packs[i] for i in sel], [(3000 + i, 1) for i in sel])
+                eq(got.Uids, orc.intersect_sorted([lists[i] for i in sel]), f"thread {t} {sel}")
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs[0]
+
+
+def test_malformed_pack_refused(dgx, orc):
+    from dgraph_b200 import _lib
+
+    u = gen.zipf_gaps(np.random.default_rng(34), 5000)
+    good = to_pack(dgx, orc.encode(u, 256))
+    eq(dgx.codec.Decode(good, 0), u, "well-formed")
+    bad = dgx.pb.UidPack(good.block_size, good.base, good.num_uids, good.delta_off.copy(), good.deltas)
+    bad.delta_off[3] = bad.delta_off[2] + 2          # block 2 shorter than its groups need
+    with pytest.raises(_lib.DgxError) as ei:
+        dgx.codec.Decode(bad, 0)
+    assert ei.value.code == -3
+    bad2 = dgx.pb.UidPack(good.block_size, good.base, good.num_uids, good.delta_off.copy(), good.deltas)
+    bad2.delta_off[5] = bad2.delta_off[4] - 1        # offsets go backwards
+    with pytest.raises(_lib.DgxError):
+        dgx.codec.Decode(bad2, 0)
+    # tags that claim more bytes than the block holds: memory-safe, library usable afterwards
+    evil = dgx.pb.UidPack(good.block_size, good.base, good.num_uids, good.delta_off, np.full_like(good.deltas, 0xFF))
+    out = dgx.codec.Decode(evil, 0)
+    assert out.size == u.size
+    eq(dgx.codec.Decode(good, 0), u, "after corrupt input")
+    # deltas summing past 2^32 inside one block follow the reference's 64-bit running sum (codec.go:191-196)
+    base = np.array([5], np.uint64)
+    num = np.array([9], np.uint32)
+    deltas = np.array([0xFF] + [0xFF] * 16 + [0xFF] + [0xFF] * 16, np.uint8)
+    p = dgx.pb.UidPack(256, base, num, np.array([0, deltas.size], np.uint64), deltas)
+    want = 5 + np.arange(9, dtype=np.uint64) * np.uint64(0xFFFFFFFF)
+    eq(dgx.codec.Decode(p, 0), want, "64-bit running sum")
+
+
+# ---- IndexOf batch, shared-list batch ----------------------------------------------------------------
+
+def test_index_of_batch(dgx, orc):
+    rng = np.random.default_rng(35)
+    for n, m in ((0, 10), (1, 5), (1000, 0), (1000, 3000), (300_000, 200_000), (5, 100_000)):
+        u = gen.uniform_unique(rng, n, max(4 * n, 16))
+        q = rng.integers(0, max(4 * n, 16) + 3, m, dtype=np.uint64)       # unsorted probes, ~25 % hits
+        if n and m:
+            q[:: 7] = u[rng.integers(0, n, q[::7].size)]
+        got = dgx.algo.IndexOfBatch(L(dgx, u), q)
+        want = np.array([orc.index_of(u, int(x)) for x in q[:2000]], dtype=np.int64)
+        assert np.array_equal(got[: want.size], want), f"IndexOf n={n} m={m}"
+        if n:
+            pos = np.searchsorted(u, q)
+            ok = (pos < n) & (u[np.minimum(pos, n - 1)] == q)
+            assert np.array_equal(got, np.where(ok, pos, -1)), f"IndexOf n={n} m={m} (all)"
+        else:
+            assert np.all(got == -1)
+    # duplicates in u: sort.Search finds the first copy
+    u = np.array([1, 3, 3, 3, 9, 9], np.uint64)
+    assert dgx.algo.IndexOfBatch(L(dgx, u), [3, 9, 1, 2]).tolist() == [1, 4, 0, -1]
+
+
+def test_intersect_batch_shared(dgx, orc):
+    rng = np.random.default_rng(36)
+    master = gen.zipf_gaps(rng, 500_000)
+    dest = gen.thin(rng, master, 0.3)
+    rows = [gen.thin(rng, master, float(p)) for p in rng.uniform(0.0005, 0.2, 200)] + [np.zeros(0, np.uint64), dest.copy()]
+    a = np.concatenate(rows)
+    a_off = np.concatenate([[0], np.cumsum([r.size for r in rows])]).astype(np.uint64)
+    out, off = dgx.algo.IntersectBatchShared(a, a_off, dest)
+    for i, r in enumerate(rows):
+        eq(out[int(off[i]): int(off[i + 1])], orc.intersect_with(r, dest), f"shared row {i}")
+    out, off = dgx.algo.IntersectBatchShared(a, a_off, np.zeros(0, np.uint64))
+    assert out.size == 0 and np.all(off == 0)
+
+
+# ---- BASELINE configs at full size --------------------------------------------------------------------
+
+def test_config3_full(dgx, orc):
+    """configs[2]: codec.Decode(UidPack blockSize=256) of 1e8 UIDs -> IntersectSorted([decoded, L1, L2])."""
+    rng = np.random.default_rng(301)
+    master = gen.zipf_gaps(rng, 100_000_000)
+    pack = orc.encode(master, 256)
+    assert orc.exact_len(pack) == master.size
+    p = to_pack(dgx, pack)
+    dec = dgx.codec.Decode(p, 0)
+    same(dec, master, "C3 decode 1e8")          # round trip == oracle decode (checked below on a seek)
+    l1 = gen.thin(np.random.default_rng(302), master, 0.1)
+    l2 = gen.thin(np.random.default_rng(303), master, 0.01)
+    got = dgx.codec.DecodeIntersectSorted(p, 0, [L(dgx, l1), L(dgx, l2)])
+    same(got.Uids, orc.intersect_sorted([master, l1, l2]), "C3 pipeline")
+    seek = int(master[60_000_000]) + 1
+    same(dgx.codec.Decode(p, seek), orc.decode(pack, seek), "C3 decode from seek")
+    o = dgx.pb.List(None)
+    dgx.algo.IntersectCompressedWith(p, seek, L(dgx, l2), o)
+    same(o.Uids, orc.intersect_compressed_with(pack, seek, l2), "C3 IntersectCompressedWith")
+
+
+def c4_pairs(npairs, seed=401):
+    """configs[3]: sizes i.i.d. truncated power law alpha=2 on [1e4, 1e6]; each pair two
+    thinnings (p=0.5) of a Zipf-gap master -- here a random window of one shared 4e6 master (drawing
+    10k separate masters would take minutes on the host), re-based per pair."""
+    rng = np.random.default_rng(seed)
+    lo, hi = 1e4, 1e6
+    uu = rng.random(npairs)
+    sizes = (1.0 / (1.0 / lo - uu * (1.0 / lo - 1.0 / hi))).astype(np.int64)   # inverse CDF of x^-2 on [lo, hi]
+    big = gen.zipf_gaps(np.random.default_rng(seed + 1), 4_000_000)
+    a_rows, b_rows = [], []
+    for n in sizes:
+        w = int(min(2 * n, big.size))
+        s0 = int(rng.integers(0, big.size - w + 1))
+        win = big[s0: s0 + w]
+        bits = np.unpackbits(np.frombuffer(rng.bytes((2 * w + 7) // 8), dtype=np.uint8))   # p = 0.5 coin flips
+        a_rows.append(win[bits[:w].view(bool)])
+        b_rows.append(win[bits[w: 2 * w].view(bool)])
+    return a_rows, b_rows
+
+
+def test_config4_full(dgx, orc):
+    """configs[3]: 10k independent 2-way intersections, 1e4-1e6 UIDs each, one batched call."""
+    a_rows, b_rows = c4_pairs(10_000)
+    a = np.concatenate(a_rows)
+    b = np.concatenate(b_rows)
+    a_off = np.concatenate([[0], np.cumsum([r.size for r in a_rows])]).astype(np.uint64)
+    b_off = np.concatenate([[0], np.cumsum([r.size for r in b_rows])]).astype(np.uint64)
+    out, off = dgx.algo.IntersectBatch(a, a_off, b, b_off)
+    want = [orc.intersect_with(x, y) for x, y in zip(a_rows, b_rows)]
+    want_off = np.concatenate([[0], np.cumsum([w.size for w in want])]).astype(np.uint64)
+    assert np.array_equal(off, want_off), "C4 CSR offsets"
+    same(out, np.concatenate(want), "C4 values")
+
+
+def test_config5_full(dgx, orc):
+    """configs[4]: MergeSorted of k=64 lists (lengths ~ 1/rank, sum 1e8, thinnings of a 2e8 master) then
+    Difference against a 1e7 thinning."""
+    rng = np.random.default_rng(501)
+    master = gen.zipf_gaps(rng, 200_000_000)
+    w = 1.0 / np.arange(1, 65)
+    lens = (w / w.sum() * 1e8).astype(np.int64)
+    # a thinning of the master with about n survivors, drawn as sorted distinct random positions (64
+    # Bernoulli passes over 2e8 values would take minutes on the host)
+    lists = [master[np.unique(rng.integers(0, master.size, int(n)))] for n in lens]
+    merged = dgx.algo.MergeSorted([L(dgx, l) for l in lists])
+    want = orc.merge_sorted(lists)
+    same(merged.Uids, want, "C5 MergeSorted")
+    d = gen.thin(np.random.default_rng(502), master, 0.05)
+    got = dgx.algo.Difference(merged, L(dgx, d))
+    same(got.Uids, orc.difference(want, d), "C5 Difference")

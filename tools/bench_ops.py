@@ -23,6 +23,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from dgraph_b200 import _lib  # noqa: E402
 
 DEV = torch.device("cuda", 0)
@@ -47,8 +48,11 @@ def thin_gpu(master, p, gen):
 
 
 class Lane:
-    def __init__(self):
-        self.lib = _lib.load()
+    def __init__(self, lib=None, handle=None):
+        self.lib = lib or _lib.load()
+        if handle is not None:   # bench.py's lane (already bound to torch's current stream)
+            self.h = handle
+            return
         _lib.check(self.lib.dgx_init(0))
         self.stream = torch.cuda.Stream(device=DEV)
         torch.cuda.set_stream(self.stream)
@@ -88,6 +92,9 @@ def timeit(fn, warm=3, reps=10):
     return float(np.median(ts)), ts
 
 
+QUIET = False
+
+
 def row(name, cfg, ms, uids_in, algo_bytes, ok, extra=None):
     peak, src = peak_gbs()
     gbs = algo_bytes / (ms * 1e-3) / 1e9
@@ -96,8 +103,20 @@ def row(name, cfg, ms, uids_in, algo_bytes, ok, extra=None):
          "peak_GBps": peak, "peak_source": src, "check": ok}
     if extra:
         r.update(extra)
-    print(json.dumps(r), flush=True)
+    if not QUIET:
+        print(json.dumps(r), flush=True)
     return r
+
+
+def quick_rows(lib, lane, dev, peak):
+    """bench.py's `ops` key: one compact line per BASELINE config other than the headline, full sizes,
+    device-resident, CUDA events, independent torch check; no CPU legs (bench.py has its own)."""
+    global DEV, QUIET
+    DEV, QUIET = dev, True
+    rows = run(Lane(lib, lane), 1, quick=True)
+    return [{"op": r["op"], "config": r["config"], "ms": round(r["ms"], 4), "uids_per_s": r["uids_per_s"],
+             "algorithmic_GBps": round(r["algorithmic_GBps"], 1), "frac_of_hbm_peak": round(r["algorithmic_GBps"] / peak, 4),
+             "check": r["check"]} for r in rows]
 
 
 def main():
@@ -105,8 +124,16 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--small", action="store_true", help="1/10 sizes (quick functional pass)")
     args = ap.parse_args()
-    S = 10 if args.small else 1
-    L = Lane()
+    rows = run(Lane(), 10 if args.small else 1, quick=False)
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+def run(L, S, quick):
+    import gen as hostgen
+
+    small = S > 1
     gen = torch.Generator(device=DEV)
     gen.manual_seed(1234)
     rows = []
@@ -114,7 +141,7 @@ def main():
     # ---- C1: 2-way IntersectWith, 2 x 1e5 uniform in [0, 1e7): single call latency + batched x2048
     n1 = 100_000
     pairs = []
-    for i in range(2048 // S):
+    for i in range((512 if quick else 2048) // S):
         a = torch.unique(torch.randint(0, 10_000_000, (int(n1 * 1.02),), device=DEV, generator=gen))[:n1].contiguous()
         b = torch.unique(torch.randint(0, 10_000_000, (int(n1 * 1.02),), device=DEV, generator=gen))[:n1].contiguous()
         pairs.append((a, b))
@@ -144,7 +171,7 @@ def main():
     del pairs, lists
 
     # ---- C2 dense variant: k=8, thinnings p=0.9 of a 1.11e6 master, 16 queries
-    Q = 16 // (4 if args.small else 1)
+    Q = 16 // (4 if small else 1)
     lists, koff, wants = [], [0], []
     for q in range(Q):
         master = zipf_gaps_gpu(1_110_000, gen)
@@ -167,7 +194,7 @@ def main():
     del lists
 
     # ---- C4 (single GPU share): batched 2-way, sizes ~ power law alpha=2 on [1e4, 1e6]
-    npairs = 10_000 // (8 * S)  # one GPU's share of the 10k-pair batch at 8 GPUs
+    npairs = 10_000 // S  # the whole 10k-pair batch on one GPU (~7.7 GB of lists)
     rng = np.random.default_rng(401)
     u = rng.random(npairs)
     sizes = np.minimum((1e4 / (1 - u * (1 - 1e4 / 1e6))).astype(np.int64), 1_000_000)
@@ -187,7 +214,7 @@ def main():
         a, b = lists[2 * i], lists[2 * i + 1]
         ok = ok and bool(torch.equal(out[offc[i]:offc[i + 1]], a[torch.isin(a, b, assume_unique=True)]))
     tot = sum(t.numel() for t in lists)
-    rows.append(row("IntersectWith (batch, skewed sizes)", f"C4 share: {npairs} pairs, sizes ~ power law on [1e4,1e6], thinnings p=0.5",
+    rows.append(row("IntersectWith (batch, skewed sizes)", f"C4: {npairs} pairs in one launch, sizes ~ power law alpha=2 on [1e4,1e6], thinnings p=0.5",
                     ms, tot, 8 * (tot + int(offc[-1])), ok, {"total_uids": tot}))
     del lists, out
 
@@ -206,8 +233,8 @@ def main():
     want = torch.unique(torch.cat(lists))
     ok = bool(nm == want.numel() and torch.equal(out[:nm], want))
     del want
-    rows.append(row("MergeSorted", f"C5: k=64 lists, lengths ~ 1/rank, total {tot} UIDs (thinnings of a {master.numel()} master); pairwise merge tree, 6 levels",
-                    ms, tot, 8 * (tot + nm), ok, {"out": nm, "launches": 6}))
+    rows.append(row("MergeSorted", f"C5: k=64 lists, lengths ~ 1/rank, total {tot} UIDs (thinnings of a {master.numel()} master); single-pass multiway merge (merge_multi.cuh)",
+                    ms, tot, 8 * (tot + nm), ok, {"out": nm}))
     dlist = thin_gpu(master, 10_000_000 / S / master.numel(), gen)
     merged = out[:nm].clone()
     dout = torch.empty(nm + 8, dtype=torch.int64, device=DEV)
@@ -222,14 +249,15 @@ def main():
     del lists, out, merged, dout, want, master
 
     # ---- C3: codec.Decode of a 1e8-UID pack (BlockSize 256), then IntersectSorted with 1e7 and 1e6 lists
-    from oracle import pyoracle as orc
-
     n3 = 100_000_000 // S
     master = zipf_gaps_gpu(n3, gen)
     host = master.cpu().numpy().view(np.uint64)
-    t0 = time.perf_counter()
-    pack = orc.encode(host, 256)
-    t_enc = time.perf_counter() - t0
+
+    class _P:  # the pack's arrays (numpy generator, tests/gen.py; byte-identical to the oracle's Encode)
+        pass
+    pack = _P()
+    _, pack.base, pack.num_uids, pack.delta_off, pack.deltas = hostgen.encode_pack_np_parallel(host, 256, threads=min(32, os.cpu_count() or 1))
+    pack.nblocks = pack.base.size
     view = _lib.PackView()
     base, num, doff_, deltas = pack.base, pack.num_uids, pack.delta_off, pack.deltas
     view.block_size, view.nblocks = 256, pack.nblocks
@@ -246,16 +274,20 @@ def main():
     ms, _ = timeit(dec, warm=2, reps=5)
     L.sync()
     ok = bool(int(out_len.item()) == n3 and torch.equal(out[:n3], master))
-    t0 = time.perf_counter()
-    sample = host[: min(n3, 20_000_000)]
-    spack = orc.encode(sample, 256)
-    t1 = time.perf_counter()
-    orc.decode(spack, 0)
-    t_dec_cpu = time.perf_counter() - t1
+    extra = {"pack_bytes": pack_bytes}
+    if not quick:
+        from oracle import pyoracle as orc   # CPU comparison leg only
+
+        sample = host[: min(n3, 20_000_000)]
+        t0 = time.perf_counter()
+        spack = orc.encode(sample, 256)
+        t_enc = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        orc.decode(spack, 0)
+        t_dec_cpu = time.perf_counter() - t1
+        extra.update({"cpu_oracle_decode_uids_per_s": sample.size / t_dec_cpu, "cpu_oracle_encode_uids_per_s": sample.size / t_enc})
     rows.append(row("codec.Decode", f"C3: {n3}-UID pack, BlockSize 256, {pack.nblocks} blocks, {deltas.size / n3:.3f} delta bytes/UID",
-                    ms, n3, pack_bytes + 8 * n3, ok,
-                    {"pack_bytes": pack_bytes, "cpu_oracle_decode_uids_per_s": sample.size / t_dec_cpu,
-                     "cpu_oracle_encode_uids_per_s": n3 / t_enc}))
+                    ms, n3, pack_bytes + 8 * n3, ok, extra))
     l1 = thin_gpu(master, 0.1, gen)
     l2 = thin_gpu(master, 0.01, gen)
     decoded = out[:n3]
@@ -272,6 +304,8 @@ def main():
     rows.append(row("Decode + IntersectSorted (pipeline)", "C3 end to end on device: decode to HBM, then intersect",
                     ms + ms_i, tot, pack_bytes + 8 * n3 + 8 * (tot + ni), ok))
     L.lib.dgx_dev_pack_free(pk)
+    if quick:
+        return rows
 
     # ---- C3 end to end through the host-pointer C ABI: the pack crosses PCIe COMPRESSED ---------
     # (dgx_decode_intersect_sorted: H2D of the pack + the two lists, decode and intersect on the
@@ -333,10 +367,7 @@ def main():
                     {"speedup_vs_cpu_1thread": (t_dec + t_int) / t_pin, "cpu_oracle_ms": (t_dec + t_int) * 1e3}))
     for ptr in pins:
         L.lib.dgx_host_free(ptr)
-
-    if args.out:
-        with open(args.out, "w") as f:
-            json.dump(rows, f, indent=1)
+    return rows
 
 
 if __name__ == "__main__":
