@@ -181,6 +181,143 @@ def kernel_source_sha() -> str:
     return h.hexdigest()[:16]
 
 
+def run_e2e_legs(args, lib, queries, want, uids_all, uids_per_step, rank, world, dev):
+    """The three end-to-end legs (packs / named packs / decoded lists) through the host-pointer C ABI."""
+    import torch
+    import torch.distributed as dist
+
+    import gen
+    from dgraph_b200 import _lib
+
+    Q = len(queries)
+
+    T = max(1, args.e2e_threads)
+    res_cap = max(min(l.size for l in qq) for qq in queries)
+    pool = ThreadPoolExecutor(max_workers=T)
+    outs = [(lib.dgx_host_alloc(res_cap * 8), C.c_size_t(0)) for _ in range(T)]
+    pinned = []
+
+    def pin(a: np.ndarray):
+        p = lib.dgx_host_alloc(max(a.nbytes, 16))
+        assert p
+        C.memmove(p, a.ctypes.data, a.nbytes)
+        pinned.append(p)
+        return p
+
+    def run_e2e(call, nsteps):
+        """`call(slot, qi)` = one query through the C ABI on thread `slot`; returns (seconds per step, out values per step).
+        The reference is called from many goroutines at once (x.DivideAndRule, worker/task.go:816); here T host
+        threads issue the queries, each call borrowing its own lane, so one query's sync gap is another's copy."""
+        def worker(slot):
+            return sum(call(slot, qi) for qi in range(slot, Q, T))
+
+        def one_step():
+            return sum(pool.map(worker, range(T)))
+        one_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            outn = one_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt / nsteps, outn
+
+    def check_e2e(call):
+        ok = True
+        for qi in range(Q):
+            n = call(0, qi)
+            got = np.ctypeslib.as_array(C.cast(outs[0][0], C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n]
+            ok = ok and np.array_equal(got, want[qi])
+        return bool(ok)
+
+    # (a) packs: what production holds.  numpy generator (tests/gen.encode_pack_np, checked against the oracle's
+    #     Encode byte for byte in tests/test_gen_encoder.py); arrays live in dgx_host_alloc (pinned) memory.
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        enc = list(ex.map(lambda l: gen.encode_pack_np(l, 256), [l for qq in queries for l in qq]))
+    views, pack_bytes = [], 0
+    for (bs, base, num, doff_, deltas) in enc:
+        v = _lib.PackView()
+        v.block_size, v.nblocks = bs, base.size
+        v.base, v.num_uids, v.delta_off, v.deltas = pin(base), pin(num), pin(doff_), pin(deltas)
+        pack_bytes += base.nbytes + num.nbytes + doff_.nbytes + deltas.nbytes
+        views.append(v)
+    del enc
+
+    def make_refs(named: bool):
+        tabs = []
+        for qi in range(Q):
+            refs = (_lib.PackRef * K_LISTS)()
+            for j in range(K_LISTS):
+                refs[j].pack = C.pointer(views[qi * K_LISTS + j])
+                refs[j].key = (1 + rank * 1_000_000 + qi * K_LISTS + j) if named else 0
+                refs[j].version = 1
+            tabs.append(refs)
+        return tabs
+
+    def packed_call(tabs):
+        def call(slot, qi):
+            buf, cnt = outs[slot]
+            _lib.check(lib.dgx_intersect_sorted_packed(tabs[qi], K_LISTS, buf, res_cap, C.byref(cnt)))
+            return cnt.value
+        return call
+
+    anon, named = make_refs(False), make_refs(True)
+    ok_packed = check_e2e(packed_call(anon))
+    s_packed, outn = run_e2e(packed_call(anon), args.e2e_steps)
+    e2e = {"value": uids_all / s_packed, "unit": UNIT, "h2d_bytes_per_step": int(pack_bytes),
+           "d2h_bytes_per_step": int(outn * 8 + 8 * Q), "ms_per_step": 1e3 * s_packed, "bit_exact": ok_packed,
+           "api": f"dgx_intersect_sorted_packed: every list a pb.UidPack (BlockSize 256, {pack_bytes / uids_per_step:.2f} B/UID) in pinned host "
+                  f"memory, copied, decoded and intersected on the device every step (no caching), one call per query, {T} host threads",
+           "pcie_GBps": pack_bytes / s_packed / 1e9}
+    lib.dgx_cache_clear()
+    ok_cached = check_e2e(packed_call(named))               # first pass fills the cache
+    st = _lib.CacheStats()
+    lib.dgx_cache_get_stats(C.byref(st))
+    h0 = _lib.stats()["h2d_bytes"]
+    s_cached, outn_c = run_e2e(packed_call(named), args.e2e_steps)
+    h2d_cached = (_lib.stats()["h2d_bytes"] - h0) / (args.e2e_steps + 1)
+    e2e_cached = {"value": uids_all / s_cached, "unit": UNIT, "h2d_bytes_per_step": int(h2d_cached),
+                  "d2h_bytes_per_step": int(outn_c * 8 + 8 * Q), "ms_per_step": 1e3 * s_cached, "bit_exact": ok_cached,
+                  "api": "dgx_intersect_sorted_packed with (key, version) on every pack: packs resident in HBM (compressed) after "
+                         "their first use, steady state; only descriptors and results cross PCIe",
+                  "cache_bytes": int(st.bytes), "cache_entries": int(st.entries)}
+    lib.dgx_cache_clear()
+    for p in pinned:
+        lib.dgx_host_free(p)
+    pinned.clear()
+
+    # (b) decoded uint64 lists over PCIe (8 B/UID): the round-1 contract, kept for comparison
+    tables = []
+    for qq in queries:
+        tables.append(((C.c_void_p * K_LISTS)(*[pin(l) for l in qq]), (C.c_size_t * K_LISTS)(*[l.size for l in qq])))
+
+    def raw_call(slot, qi):
+        buf, cnt = outs[slot]
+        tp, tl = tables[qi]
+        _lib.check(lib.dgx_intersect_sorted(tp, tl, K_LISTS, buf, res_cap, C.byref(cnt)))
+        return cnt.value
+
+    ok_raw = check_e2e(raw_call)
+    s_raw, outn_r = run_e2e(raw_call, max(2, args.e2e_steps // 2))
+    e2e_raw = {"value": uids_all / s_raw, "unit": UNIT, "h2d_bytes_per_step": int(uids_per_step * 8),
+               "d2h_bytes_per_step": int(outn_r * 8 + 8 * Q), "ms_per_step": 1e3 * s_raw, "bit_exact": ok_raw,
+               "api": f"dgx_intersect_sorted (decoded uint64 lists in pinned host memory, 8 B/UID over PCIe), one call per query, {T} host threads",
+               "pcie_GBps": uids_per_step * 8 / s_raw / 1e9}
+    for p in pinned:
+        lib.dgx_host_free(p)
+    for buf, _ in outs:
+        lib.dgx_host_free(buf)
+    pool.shutdown()
+    return e2e, e2e_cached, e2e_raw, bool(ok_packed and ok_cached and ok_raw)
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +330,7 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=8)
     ap.add_argument("--no-ops", action="store_true", help="skip the per-config (C1/C3/C4/C5) one-liners under `ops`")
     ap.add_argument("--no-dense", action="store_true", help="skip the p=0.9 variant of the headline step")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel iteration runs only: skip the end-to-end legs (the line then has no e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -420,133 +558,10 @@ def main():
         del dk, dbuf
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ------
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import gen
-
-    T = max(1, args.e2e_threads)
-    res_cap = max(min(l.size for l in qq) for qq in queries)
-    pool = ThreadPoolExecutor(max_workers=T)
-    outs = [(lib.dgx_host_alloc(res_cap * 8), C.c_size_t(0)) for _ in range(T)]
-    pinned = []
-
-    def pin(a: np.ndarray):
-        p = lib.dgx_host_alloc(max(a.nbytes, 16))
-        assert p
-        C.memmove(p, a.ctypes.data, a.nbytes)
-        pinned.append(p)
-        return p
-
-    def run_e2e(call, nsteps):
-        """`call(slot, qi)` = one query through the C ABI on thread `slot`; returns (seconds per step, out values per step).
-        The reference is called from many goroutines at once (x.DivideAndRule, worker/task.go:816); here T host
-        threads issue the queries, each call borrowing its own lane, so one query's sync gap is another's copy."""
-        def worker(slot):
-            return sum(call(slot, qi) for qi in range(slot, Q, T))
-
-        def one_step():
-            return sum(pool.map(worker, range(T)))
-        one_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(nsteps):
-            outn = one_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt / nsteps, outn
-
-    def check_e2e(call):
-        ok = True
-        for qi in range(Q):
-            n = call(0, qi)
-            got = np.ctypeslib.as_array(C.cast(outs[0][0], C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n]
-            ok = ok and np.array_equal(got, want[qi])
-        return bool(ok)
-
-    # (a) packs: what production holds.  numpy generator (tests/gen.encode_pack_np, checked against the oracle's
-    #     Encode byte for byte in tests/test_gen_encoder.py); arrays live in dgx_host_alloc (pinned) memory.
-    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-        enc = list(ex.map(lambda l: gen.encode_pack_np(l, 256), [l for qq in queries for l in qq]))
-    views, pack_bytes = [], 0
-    for (bs, base, num, doff_, deltas) in enc:
-        v = _lib.PackView()
-        v.block_size, v.nblocks = bs, base.size
-        v.base, v.num_uids, v.delta_off, v.deltas = pin(base), pin(num), pin(doff_), pin(deltas)
-        pack_bytes += base.nbytes + num.nbytes + doff_.nbytes + deltas.nbytes
-        views.append(v)
-    del enc
-
-    def make_refs(named: bool):
-        tabs = []
-        for qi in range(Q):
-            refs = (_lib.PackRef * K_LISTS)()
-            for j in range(K_LISTS):
-                refs[j].pack = C.pointer(views[qi * K_LISTS + j])
-                refs[j].key = (1 + rank * 1_000_000 + qi * K_LISTS + j) if named else 0
-                refs[j].version = 1
-            tabs.append(refs)
-        return tabs
-
-    def packed_call(tabs):
-        def call(slot, qi):
-            buf, cnt = outs[slot]
-            _lib.check(lib.dgx_intersect_sorted_packed(tabs[qi], K_LISTS, buf, res_cap, C.byref(cnt)))
-            return cnt.value
-        return call
-
-    anon, named = make_refs(False), make_refs(True)
-    ok_packed = check_e2e(packed_call(anon))
-    s_packed, outn = run_e2e(packed_call(anon), args.e2e_steps)
-    e2e = {"value": uids_all / s_packed, "unit": UNIT, "h2d_bytes_per_step": int(pack_bytes),
-           "d2h_bytes_per_step": int(outn * 8 + 8 * Q), "ms_per_step": 1e3 * s_packed, "bit_exact": ok_packed,
-           "api": f"dgx_intersect_sorted_packed: every list a pb.UidPack (BlockSize 256, {pack_bytes / uids_per_step:.2f} B/UID) in pinned host "
-                  f"memory, copied, decoded and intersected on the device every step (no caching), one call per query, {T} host threads",
-           "pcie_GBps": pack_bytes / s_packed / 1e9}
-    lib.dgx_cache_clear()
-    ok_cached = check_e2e(packed_call(named))               # first pass fills the cache
-    st = _lib.CacheStats()
-    lib.dgx_cache_get_stats(C.byref(st))
-    h0 = _lib.stats()["h2d_bytes"]
-    s_cached, outn_c = run_e2e(packed_call(named), args.e2e_steps)
-    h2d_cached = (_lib.stats()["h2d_bytes"] - h0) / (args.e2e_steps + 1)
-    e2e_cached = {"value": uids_all / s_cached, "unit": UNIT, "h2d_bytes_per_step": int(h2d_cached),
-                  "d2h_bytes_per_step": int(outn_c * 8 + 8 * Q), "ms_per_step": 1e3 * s_cached, "bit_exact": ok_cached,
-                  "api": "dgx_intersect_sorted_packed with (key, version) on every pack: packs resident in HBM (compressed) after "
-                         "their first use, steady state; only descriptors and results cross PCIe",
-                  "cache_bytes": int(st.bytes), "cache_entries": int(st.entries)}
-    lib.dgx_cache_clear()
-    for p in pinned:
-        lib.dgx_host_free(p)
-    pinned.clear()
-
-    # (b) decoded uint64 lists over PCIe (8 B/UID): the round-1 contract, kept for comparison
-    tables = []
-    for qq in queries:
-        tables.append(((C.c_void_p * K_LISTS)(*[pin(l) for l in qq]), (C.c_size_t * K_LISTS)(*[l.size for l in qq])))
-
-    def raw_call(slot, qi):
-        buf, cnt = outs[slot]
-        tp, tl = tables[qi]
-        _lib.check(lib.dgx_intersect_sorted(tp, tl, K_LISTS, buf, res_cap, C.byref(cnt)))
-        return cnt.value
-
-    ok_raw = check_e2e(raw_call)
-    s_raw, outn_r = run_e2e(raw_call, max(2, args.e2e_steps // 2))
-    e2e_raw = {"value": uids_all / s_raw, "unit": UNIT, "h2d_bytes_per_step": int(uids_per_step * 8),
-               "d2h_bytes_per_step": int(outn_r * 8 + 8 * Q), "ms_per_step": 1e3 * s_raw, "bit_exact": ok_raw,
-               "api": f"dgx_intersect_sorted (decoded uint64 lists in pinned host memory, 8 B/UID over PCIe), one call per query, {T} host threads",
-               "pcie_GBps": uids_per_step * 8 / s_raw / 1e9}
-    for p in pinned:
-        lib.dgx_host_free(p)
-    for buf, _ in outs:
-        lib.dgx_host_free(buf)
-    pool.shutdown()
-    bit_exact = bit_exact and ok_packed and ok_cached and ok_raw
+    e2e = e2e_cached = e2e_raw = None
+    if not args.no_e2e:
+        e2e, e2e_cached, e2e_raw, ok_e2e = run_e2e_legs(args, lib, queries, want, uids_all, uids_per_step, rank, world, dev)
+        bit_exact = bit_exact and ok_e2e
 
     ops = None
     if world == 1 and not args.no_ops:

@@ -803,37 +803,33 @@ struct dgx_dev_pack {
     uint32_t block_size = 0;
 };
 
-// Lays the pack out in one device allocation:
-// [base u64 | delta_off u64 (n+1) | uid_off u64 (n+1) | num u32 | deltas (16-aligned, +48 slack)]
-static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_null, DevArena* arena,
-                            dgx_dev_pack* out) {
-    const size_t nb = v ? v->nblocks : 0;
-    const size_t dbytes = nb ? (size_t)v->delta_off[nb] : 0;
-    const size_t o_base = 0;
-    const size_t o_doff = o_base + nb * 8;
-    const size_t o_uoff = o_doff + (nb + 1) * 8;
-    const size_t o_num = o_uoff + (nb + 1) * 8;
-    const size_t o_del = (o_num + nb * 4 + 15) & ~size_t(15);
-    const size_t total = o_del + ((dbytes + 15) & ~size_t(15)) + 48;
-    void* d_mem = d_mem_or_null;
-    int rc;
-    if (!d_mem) {
-        if (arena) { rc = arena->alloc(total, &d_mem); if (rc) return rc; }
-        else {
-            cudaError_t e = cudaMalloc(&d_mem, total);
-            if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
-            out->d_mem = d_mem;  // owned by *out from here on, also when a later step fails
-        }
-    }
-    // uid_off (exclusive prefix of NumUids) and max NumUids: layout metadata, computed while flattening
-    void* h_raw;
-    rc = l->host.alloc((nb + 1) * 8, &h_raw);
-    if (rc) return rc;
-    uint64_t* h_uoff = (uint64_t*)h_raw;
+// Device layout of a pack: [base u64 | delta_off u64 (n+1) | uid_off u64 (n+1) | num u32 | pad to 16]
+// followed by the delta bytes (16-byte aligned, 48 readable bytes of slack for the 16-byte TMA granule and
+// the 17-byte group reads).  The metadata image is assembled in pinned staging memory so that a pack
+// crosses PCIe as TWO copies (metadata, deltas) and the k packs of a query as 1 + k: small copies cost
+// several microseconds of DMA set-up each and used to outweigh the bytes.
+struct PackLayout {
+    size_t nb, dbytes, o_doff, o_uoff, o_num, meta_bytes, dpad;
+};
+static PackLayout pack_layout(const dgx_pack_view* v) {
+    PackLayout L;
+    L.nb = v ? v->nblocks : 0;
+    L.dbytes = L.nb ? (size_t)v->delta_off[L.nb] : 0;
+    L.o_doff = L.nb * 8;
+    L.o_uoff = L.o_doff + (L.nb + 1) * 8;
+    L.o_num = L.o_uoff + (L.nb + 1) * 8;
+    L.meta_bytes = (L.o_num + L.nb * 4 + 15) & ~size_t(15);
+    L.dpad = ((L.dbytes + 15) & ~size_t(15)) + 48;
+    return L;
+}
+// Writes the metadata image at h (L.meta_bytes) and validates the block table.
+static int pack_fill_meta(const dgx_pack_view* v, const PackLayout& L, char* h, uint64_t* exact_len, uint32_t* max_num_out) {
+    const size_t nb = L.nb;
+    uint64_t* h_uoff = (uint64_t*)(h + L.o_uoff);
     uint64_t acc = 0;
     uint32_t max_num = 0;
     for (size_t i = 0; i < nb; ++i) {
-        h_uoff[i] = acc;
+        h_uoff[i] = acc;  // uid_off: exclusive prefix of NumUids, every block's output offset
         const uint32_t num = v->num_uids[i];
         acc += num;
         max_num = std::max(max_num, num);
@@ -847,27 +843,100 @@ static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_
                         i, (long long)(b1 - b0), num, (unsigned long long)need);
     }
     h_uoff[nb] = acc;
-    char* d = (char*)d_mem;
     if (nb) {
-        CK(cudaMemcpyAsync(d + o_base, v->base, nb * 8, cudaMemcpyHostToDevice, l->stream));
-        CK(cudaMemcpyAsync(d + o_doff, v->delta_off, (nb + 1) * 8, cudaMemcpyHostToDevice, l->stream));
-        CK(cudaMemcpyAsync(d + o_num, v->num_uids, nb * 4, cudaMemcpyHostToDevice, l->stream));
-        if (dbytes) CK(cudaMemcpyAsync(d + o_del, v->deltas, dbytes, cudaMemcpyHostToDevice, l->stream));
+        memcpy(h, v->base, nb * 8);
+        memcpy(h + L.o_doff, v->delta_off, (nb + 1) * 8);
+        memcpy(h + L.o_num, v->num_uids, nb * 4);
+    } else {
+        memset(h + L.o_doff, 0, 8);
     }
-    CK(cudaMemcpyAsync(d + o_uoff, h_uoff, (nb + 1) * 8, cudaMemcpyHostToDevice, l->stream));
-    CK(cudaMemsetAsync(d + o_del + dbytes, 0, total - o_del - dbytes, l->stream));
-    g_stats.h2d += nb * 8 + (nb + 1) * 16 + nb * 4 + dbytes;
-    out->pk.nblocks = nb;
-    out->pk.base = (const u64*)(d + o_base);
-    out->pk.delta_off = (const u64*)(d + o_doff);
-    out->pk.uid_off = (const u64*)(d + o_uoff);
-    out->pk.num = (const u32*)(d + o_num);
-    out->pk.deltas = (const unsigned char*)(d + o_del);
+    *exact_len = acc;
+    *max_num_out = max_num;
+    return DGX_OK;
+}
+static void pack_point(dgx_dev_pack* out, const dgx_pack_view* v, const PackLayout& L, char* d_meta, char* d_deltas,
+                       uint64_t exact_len, uint32_t max_num) {
+    out->pk.nblocks = L.nb;
+    out->pk.base = (const u64*)d_meta;
+    out->pk.delta_off = (const u64*)(d_meta + L.o_doff);
+    out->pk.uid_off = (const u64*)(d_meta + L.o_uoff);
+    out->pk.num = (const u32*)(d_meta + L.o_num);
+    out->pk.deltas = (const unsigned char*)d_deltas;
     out->pk.max_num = max_num;
-    out->d_mem = d_mem;
-    out->bytes = total;
-    out->exact_len = acc;
+    out->bytes = L.meta_bytes + L.dpad;
+    out->exact_len = exact_len;
     out->block_size = v ? v->block_size : 0;
+}
+
+// One pack -> one device allocation (cudaMalloc when arena == nullptr: the caller owns out->d_mem).
+static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_null, DevArena* arena,
+                            dgx_dev_pack* out) {
+    const PackLayout L = pack_layout(v);
+    const size_t total = L.meta_bytes + L.dpad;
+    void* d_mem = d_mem_or_null;
+    int rc;
+    if (!d_mem) {
+        if (arena) { rc = arena->alloc(total, &d_mem); if (rc) return rc; }
+        else {
+            cudaError_t e = cudaMalloc(&d_mem, total);
+            if (e != cudaSuccess) return fail(DGX_ERR_OOM, "cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+            out->d_mem = d_mem;  // owned by *out from here on, also when a later step fails
+        }
+    }
+    void* h_raw;
+    rc = l->host.alloc(L.meta_bytes, &h_raw);
+    if (rc) return rc;
+    uint64_t exact = 0;
+    uint32_t max_num = 0;
+    rc = pack_fill_meta(v, L, (char*)h_raw, &exact, &max_num);
+    if (rc) return rc;
+    char* d = (char*)d_mem;
+    CK(cudaMemcpyAsync(d, h_raw, L.meta_bytes, cudaMemcpyHostToDevice, l->stream));
+    if (L.dbytes) CK(cudaMemcpyAsync(d + L.meta_bytes, v->deltas, L.dbytes, cudaMemcpyHostToDevice, l->stream));
+    g_stats.h2d += L.meta_bytes + L.dbytes;
+    pack_point(out, v, L, d, d + L.meta_bytes, exact, max_num);
+    out->d_mem = d_mem;
+    return DGX_OK;
+}
+
+// The k packs of one call into the lane's workspace: one copy for all metadata images, one per pack
+// for its delta bytes (straight from the caller's memory).  views[i] == nullptr entries are skipped.
+static int packs_upload_ws(dgx_lane* l, const dgx_pack_view* const* views, size_t k, dgx_dev_pack* outs) {
+    std::vector<PackLayout> Ls(k);
+    size_t meta_total = 0, del_total = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (!views[i]) continue;
+        Ls[i] = pack_layout(views[i]);
+        meta_total += Ls[i].meta_bytes;
+        del_total += Ls[i].dpad;
+    }
+    if (meta_total == 0) return DGX_OK;
+    void *d_raw, *h_raw;
+    int rc = l->ws.alloc(meta_total + del_total, &d_raw);
+    if (rc) return rc;
+    rc = l->host.alloc(meta_total, &h_raw);
+    if (rc) return rc;
+    char* d_meta = (char*)d_raw;
+    char* d_del = (char*)d_raw + meta_total;
+    char* h = (char*)h_raw;
+    size_t mo = 0, dof = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (!views[i]) continue;
+        uint64_t exact = 0;
+        uint32_t max_num = 0;
+        rc = pack_fill_meta(views[i], Ls[i], h + mo, &exact, &max_num);
+        if (rc) return rc;
+        pack_point(&outs[i], views[i], Ls[i], d_meta + mo, d_del + dof, exact, max_num);
+        outs[i].d_mem = nullptr;  // workspace memory: not owned
+        mo += Ls[i].meta_bytes;
+        dof += Ls[i].dpad;
+    }
+    CK(cudaMemcpyAsync(d_meta, h, meta_total, cudaMemcpyHostToDevice, l->stream));
+    for (size_t i = 0; i < k; ++i)
+        if (views[i] && Ls[i].dbytes)
+            CK(cudaMemcpyAsync((void*)outs[i].pk.deltas, views[i]->deltas, Ls[i].dbytes, cudaMemcpyHostToDevice, l->stream));
+    for (size_t i = 0; i < k; ++i)
+        if (views[i]) g_stats.h2d += Ls[i].meta_bytes + Ls[i].dbytes;
     return DGX_OK;
 }
 
@@ -1192,10 +1261,8 @@ extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_u
 // of its Badger key and the commit timestamp of the layer -- stays in HBM in its compressed form and
 // later calls skip the copy.  Eviction is LRU by bytes; entries in use by a running call are pinned.
 static size_t pack_device_bytes(const dgx_pack_view* v) {
-    const size_t nb = v ? v->nblocks : 0;
-    const size_t dbytes = nb ? (size_t)v->delta_off[nb] : 0;
-    const size_t o_del = (nb * 8 + (nb + 1) * 16 + nb * 4 + 15) & ~size_t(15);
-    return o_del + ((dbytes + 15) & ~size_t(15)) + 48;
+    const PackLayout L = pack_layout(v);
+    return L.meta_bytes + L.dpad;
 }
 
 struct CacheKey {
@@ -1279,7 +1346,8 @@ static void pack_release(PackLease& pl) {
     pl.entry->refs -= 1;
     pl.entry = nullptr;
 }
-static int pack_acquire(dgx_lane* l, const dgx_pack_ref& ref, PackLease* out) {
+static int pack_acquire(dgx_lane* l, const dgx_pack_ref& ref, PackLease* out, bool* deferred) {
+    *deferred = false;
     const dgx_pack_view* v = ref.pack;
     if (ref.key != 0) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -1332,7 +1400,8 @@ static int pack_acquire(dgx_lane* l, const dgx_pack_ref& ref, PackLease* out) {
         }
         // does not fit (cache disabled, pack larger than the cache, everything pinned): one-shot copy
     }
-    return pack_upload_impl(l, v, nullptr, &l->ws, &out->pk);
+    *deferred = true;  // copied into the lane's workspace together with the call's other one-shot packs
+    return DGX_OK;
 }
 
 // Decode every pack of `pls` in full, side by side, with one launch; d_lists[i] receives pack i.
@@ -1384,7 +1453,18 @@ extern "C" int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k, u
     std::vector<uint64_t*> d_lists(k, nullptr);
     int rc = DGX_OK;
     size_t got = 0;
-    for (; got < k && rc == DGX_OK; ++got) rc = pack_acquire(l, refs[got], &pls[got]);
+    std::vector<const dgx_pack_view*> oneshot(k, nullptr);
+    for (; got < k && rc == DGX_OK; ++got) {
+        bool deferred = false;
+        rc = pack_acquire(l, refs[got], &pls[got], &deferred);
+        if (deferred) oneshot[got] = refs[got].pack;
+    }
+    if (rc == DGX_OK) {
+        std::vector<dgx_dev_pack> up(k);
+        rc = packs_upload_ws(l, oneshot.data(), k, up.data());
+        for (size_t i = 0; i < k && rc == DGX_OK; ++i)
+            if (oneshot[i]) pls[i].pk = up[i];
+    }
     if (rc == DGX_OK) rc = decode_batch_impl(l, pls.data(), k, d_lists.data());
     size_t cap = SIZE_MAX;
     void *d_out = nullptr, *d_off = nullptr;

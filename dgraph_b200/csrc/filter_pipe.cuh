@@ -53,6 +53,9 @@ constexpr int P_OS = DGX_P_OS;           // output slots in flight (6 vs 4: 2-li
 #ifndef DGX_P_ST
 #define DGX_P_ST 2
 #endif
+#ifndef DGX_P_FAST
+#define DGX_P_FAST 1   // 0: build without the 32-bit fast path (A/B measurements, fallback-path tests)
+#endif
 constexpr int P_ST = DGX_P_ST;           // data stages in flight
 constexpr int P_MAXL = 8;                // filter lists a stage can hold
 constexpr int P_RING = 8;                // tile descriptors in flight between M and T
@@ -270,6 +273,70 @@ __device__ __forceinline__ bool phit(const PTile& X, u64 x, int i, unsigned dup,
     if (!((dup >> i) & 1u)) return (p < n) && (sb[p] == x);
     const u64 g = g0 + (u64)p + cand_rank(X.cand, X.cidx0 + 32 * i, x, X.has_prev, X.prev, X.A, X.a0);
     return (g < lenB) && (ld_probe(B + g) == x);
+}
+
+// ---- 32-bit fast path ---------------------------------------------------------------------
+// When every value of a tile shares its upper 32 bits (the rule for real UID ranges: a tile of 512
+// driving values rarely straddles a multiple of 2^32) the staged slices, which lie inside
+// [tile first, tile last], share them too, and membership is decided on the LOW words alone, read in
+// place (ld.shared.u32 at an 8-byte stride) with 32-bit compares.  A search is: one probe of element
+// p2-1 (p2 = largest power of two <= n) choosing the window [0, p2) or [n-p2, n), then log2(p2)
+// lifting steps with compile-time strides -- load with an immediate offset, compare, predicated add:
+// three instructions a step, against seven for the guarded 64-bit ladder (lift_multi).
+template <int OFF>
+__device__ __forceinline__ u32 lds32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ u32 lds32r(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// R rows of one lane against the slice at shared byte address sb (n >= 1 values, 8-byte stride).
+// Returns bit i set when x[i] is present.
+template <int R>
+__device__ __forceinline__ unsigned lift32(u32 sb, u32 n, const u32 (&x)[R]) {
+    const int l2 = 31 - __clz(n);
+    const u32 p2 = 1u << l2;
+    u32 a[R];
+    {
+        const u32 pivot = lds32r(sb + (p2 - 1u) * 8u);
+        const u32 hi_window = sb + (n - p2) * 8u;
+#pragma unroll
+        for (int i = 0; i < R; ++i) a[i] = pivot < x[i] ? hi_window : sb;
+    }
+#define DGX_L32(H)                                                      \
+    {                                                                   \
+        _Pragma("unroll") for (int i = 0; i < R; ++i) {                 \
+            const u32 v_ = lds32<((H) - 1) * 8>(a[i]);                  \
+            if (v_ < x[i]) a[i] += (H) * 8;                             \
+        }                                                               \
+    }
+    switch (l2) {
+        case 15: DGX_L32(16384)
+        case 14: DGX_L32(8192)
+        case 13: DGX_L32(4096)
+        case 12: DGX_L32(2048)
+        case 11: DGX_L32(1024)
+        case 10: DGX_L32(512)
+        case 9: DGX_L32(256)
+        case 8: DGX_L32(128)
+        case 7: DGX_L32(64)
+        case 6: DGX_L32(32)
+        case 5: DGX_L32(16)
+        case 4: DGX_L32(8)
+        case 3: DGX_L32(4)
+        case 2: DGX_L32(2)
+        case 1: DGX_L32(1)
+        default: break;
+    }
+#undef DGX_L32
+    unsigned hit = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) hit |= (lds32r(a[i]) == x[i]) ? (1u << i) : 0u;
+    return hit;
 }
 
 #ifdef DGX_PIPE_PROF
@@ -545,6 +612,68 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
 
             u32 t = 0;
             PPROF_PHASE(0)
+            // ---- fast path: one upper word for the whole tile, no repeated values in this warp's rows,
+            //      every filter list staged -> 32-bit searches on the low words (see lift32) ----------
+            bool fast = DGX_P_FAST && !warp_dup && nstaged == km1 && na > 0;
+            u32 hiword = 0;
+            if (fast) {
+                const u32 cb = smem_u32(cand);
+                hiword = lds32r(cb + 4u);
+                fast = hiword == lds32r(cb + (na - 1u) * 8u + 4u);
+            }
+            if (fast) {
+                u32 x[P_VA];
+#pragma unroll
+                for (int i = 0; i < P_VA; ++i) x[i] = (u32)c[i];
+                const u32 slb = smem_u32(sl);
+                const bool keep_hits = P.op == 0;
+                for (; t < km1 && rows > 0; ++t) {
+                    const u32 n = G.n[t];
+                    unsigned hit = 0;
+                    if (n != 0) {
+                        const u32 sb = slb + G.off[t] * 8u;
+                        if (rows == 1) {
+                            const u32 x1[1] = {x[0]};
+                            hit = lift32<1>(sb, n, x1);
+                        } else {
+                            hit = lift32<P_VA>(sb, n, x);
+                        }
+                    }
+                    alive &= keep_hits ? hit : ~hit;
+                    if (t + 1 < km1) {
+                        // re-pack into fewer rows (order preserved); a single row only checks for survivors
+                        unsigned b[P_VA];
+                        int tot = 0;
+#pragma unroll
+                        for (int i = 0; i < P_VA; ++i) {
+                            b[i] = __ballot_sync(0xffffffffu, (i < rows) && ((alive >> i) & 1u));
+                            tot += __popc(b[i]);
+                        }
+                        const int nrows = (tot + 31) >> 5;
+                        if (nrows == 0) { rows = 0; alive = 0; }
+                        else if (nrows < rows) {
+                            u32* s32 = reinterpret_cast<u32*>(s_w);
+                            const unsigned lt = (1u << lane) - 1u;
+                            int before = 0;
+#pragma unroll
+                            for (int i = 0; i < P_VA; ++i) {
+                                if ((b[i] >> lane) & 1u) s32[before + __popc(b[i] & lt)] = x[i];
+                                before += __popc(b[i]);
+                            }
+                            __syncwarp();
+                            alive = 0;
+#pragma unroll
+                            for (int i = 0; i < P_VA; ++i)
+                                if (i < nrows && 32 * i + lane < tot) { x[i] = s32[32 * i + lane]; alive |= 1u << i; }
+                            __syncwarp();
+                            rows = nrows;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < P_VA; ++i) c[i] = ((u64)hiword << 32) | (u64)x[i];
+                t = km1;
+            }
             while (t < km1 && rows > 0) {
                 if (t < nstaged) {
                     if (rows == 2 || t + 1 >= nstaged) {
