@@ -68,6 +68,8 @@ SYMBOLS = {
     "dgx_decode_intersect_sorted": (_int, [C.POINTER(PackView), _u64, _vp, _vp, _sz, _vp, _sz, _szp]),
     "dgx_intersect_compressed": (_int, [C.POINTER(PackView), _u64, _vp, _sz, _vp, _sz, _szp]),
     "dgx_intersect_sorted_packed": (_int, [C.POINTER(PackRef), _sz, _vp, _sz, _szp]),
+    "dgx_intersect_compressed_ref": (_int, [C.POINTER(PackRef), _u64, _vp, _sz, _vp, _sz, _szp]),
+    "dgx_pack_seek": (_int, [C.POINTER(PackView), _int, _u64, _int, _sz, _vp, _sz, _szp, _szp]),
     "dgx_cache_configure": (_int, [_sz]),
     "dgx_cache_clear": (None, []),
     "dgx_cache_get_stats": (None, [C.POINTER(CacheStats)]),

@@ -69,3 +69,66 @@ def DecodeIntersectSorted(pack: Optional[UidPack], seek: int, lists: Sequence[Li
         vp = C.byref(v)
     _lib.check(lib.dgx_decode_intersect_sorted(vp, seek, ptrs, lens, k, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
     return List(out[: n.value])
+
+
+SeekStart, SeekCurrent = 0, 1  # codec.SeekStart / codec.SeekCurrent (codec/codec.go:29-36)
+_SK_SEEK, _SK_SEEK_TO_BLOCK, _SK_LINEAR_SEEK, _SK_NEXT, _SK_UNPACK = range(5)
+
+
+class Decoder:
+    """codec.Decoder (codec/codec.go:139-384) over libdgx: every positioned call is ONE C-ABI call
+    (dgx_pack_seek) evaluated on the device; this object only carries what the Go struct carries
+    between calls -- the pack, blockIdx and the current uid slice."""
+
+    def __init__(self, pack: Optional[UidPack]):
+        self.Pack = None if pack is None else pack.normalized()
+        self.blockIdx = 0
+        self.uids = np.zeros(0, dtype=np.uint64)
+
+    def _call(self, kind: int, uid: int = 0, whence: int = 0) -> np.ndarray:
+        if self.Pack is None or self.Pack.nblocks == 0:
+            self.uids = np.zeros(0, dtype=np.uint64)
+            return self.uids
+        lib = _lib.load()
+        cap = max(int(self.Pack.num_uids.max()), 1)
+        out = np.empty(cap, dtype=np.uint64)
+        n, blk = C.c_size_t(0), C.c_size_t(0)
+        v = view_of(self.Pack)
+        _lib.check(lib.dgx_pack_seek(C.byref(v), kind, uid, whence, self.blockIdx,
+                                     out.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(blk)))
+        self.blockIdx = blk.value
+        self.uids = out[: n.value]
+        return self.uids
+
+    def UnpackBlock(self) -> np.ndarray:
+        return self._call(_SK_UNPACK)
+
+    def Seek(self, uid: int, whence: int) -> np.ndarray:
+        return self._call(_SK_SEEK, uid, whence)
+
+    def SeekToBlock(self, uid: int, whence: int) -> np.ndarray:
+        return self._call(_SK_SEEK_TO_BLOCK, uid, whence)
+
+    def LinearSeek(self, seek: int) -> np.ndarray:
+        return self._call(_SK_LINEAR_SEEK, seek)
+
+    def Next(self) -> np.ndarray:
+        return self._call(_SK_NEXT)
+
+    def Uids(self) -> np.ndarray:
+        return self.uids
+
+    def BlockIdx(self) -> int:
+        return self.blockIdx
+
+    def Valid(self) -> bool:
+        return self.Pack is not None and self.blockIdx < self.Pack.nblocks
+
+    def PeekNextBase(self) -> int:
+        b = self.blockIdx + 1
+        if self.Pack is not None and b < self.Pack.nblocks:
+            return int(self.Pack.base[b])
+        return 0xFFFFFFFFFFFFFFFF
+
+    def ApproxLen(self) -> int:
+        return 0 if self.Pack is None else int(self.Pack.block_size) * (self.Pack.nblocks - self.blockIdx)

@@ -30,6 +30,7 @@
 #include "merge_kernel.cuh"
 #include "merge_multi.cuh"
 #include "probe_kernel.cuh"
+#include "compressed_kernel.cuh"
 #include "wire.hpp"
 
 using namespace dgx;
@@ -219,6 +220,8 @@ extern "C" int dgx_init(int device) {
     CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sizeof(DWarpSmem) * D_WARPS)));
     CK(cudaFuncSetAttribute(decode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(sizeof(DWarpSmem) * D_WARPS)));
+    CK(cudaFuncSetAttribute(icw_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sizeof(DWarpSmem) * D_WARPS)));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * F_TA * sizeof(u64) + kScapMax)));
@@ -1241,15 +1244,69 @@ extern "C" int dgx_decode_intersect_sorted(const dgx_pack_view* p, uint64_t seek
     return finish_to_host(l, (uint64_t*)d_off + 1, (uint64_t*)d_out, cap, out, out_cap, out_len);
 }
 
-extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
-                                        uint64_t* out, size_t out_cap, size_t* out_len) {
-    if (p == nullptr) {  // `if pack == nil { return }` (algo/uidlist.go:34-36): o is left untouched -> length 0 here
-        if (out_len) *out_len = 0;
+// algo.IntersectCompressedWith on the device (compressed_kernel.cuh): v-ranges of the blocks, decode +
+// probe of the touched blocks in shared memory, order-preserving compaction of v.
+static int icw_impl(dgx_lane* l, const dgx_dev_pack& pk, uint64_t after, const uint64_t* d_v, size_t m,
+                    uint64_t* d_out, size_t out_cap, uint64_t* d_len) {
+    const size_t nb = pk.pk.nblocks;
+    if (nb == 0 || m == 0) {
+        CK(cudaMemsetAsync(d_len, 0, sizeof(uint64_t), l->stream));
         return DGX_OK;
     }
-    const uint64_t* lists[1] = {v};
-    const size_t lens[1] = {m};
-    return dgx_decode_intersect_sorted(p, after_uid, lists, lens, 1, out, out_cap, out_len);
+    const size_t tiles = (m + CP_TILE - 1) / CP_TILE;
+    const size_t b_rng = ((2 * nb * sizeof(u32)) + 15) & ~size_t(15);
+    const size_t b_keep = (m + 15) & ~size_t(15);
+    const size_t b_stat = tiles * sizeof(u64) + 64;
+    void* d_raw;
+    int rc = l->ws.alloc(b_rng + b_keep + b_stat, &d_raw);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_raw, 0, b_rng + b_keep + b_stat, l->stream));
+    IcwParams P;
+    P.pk = pk.pk;
+    P.v = (const u64*)d_v;
+    P.m = m;
+    P.after = after;
+    P.vlo = (u32*)d_raw;
+    P.vhi = P.vlo + nb;
+    P.keep = (unsigned char*)d_raw + b_rng;
+    // search the shorter side's elements in the longer side (the reference's linVsBinRatio idea, :49-59)
+    if (m < nb) icw_ranges_by_v_kernel<<<(unsigned)((m + 255) / 256), 256, 0, l->stream>>>(P);
+    else icw_ranges_by_block_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
+    CK(cudaGetLastError());
+    const uint64_t warps = (nb + D_BPW - 1) / D_BPW;
+    icw_probe_kernel<<<(unsigned)((warps + D_WARPS - 1) / D_WARPS), D_NT, sizeof(DWarpSmem) * D_WARPS, l->stream>>>(P);
+    CK(cudaGetLastError());
+    CompactParams C;
+    C.v = (const u64*)d_v;
+    C.keep = P.keep;
+    C.m = m;
+    C.out = (u64*)d_out;
+    C.out_cap = out_cap;
+    C.out_len = (u64*)d_len;
+    C.status = (u64*)((char*)d_raw + b_rng + b_keep);
+    C.ticket = (u32*)((char*)d_raw + b_rng + b_keep + tiles * sizeof(u64));
+    C.err = l->d_err;
+    compact_kernel<<<(unsigned)tiles, CP_NT, 0, l->stream>>>(C);
+    CK(cudaGetLastError());
+    l->launches += 3;
+    g_stats.launches += 3;
+    g_stats.uids_in += pk.exact_len + m;
+    return DGX_OK;
+}
+
+struct PackLease;
+static int intersect_compressed_host(const dgx_pack_ref& ref, uint64_t after_uid, const uint64_t* v, size_t m,
+                                     uint64_t* out, size_t out_cap, size_t* out_len);
+
+extern "C" int dgx_intersect_compressed(const dgx_pack_view* p, uint64_t after_uid, const uint64_t* v, size_t m,
+                                        uint64_t* out, size_t out_cap, size_t* out_len) {
+    const dgx_pack_ref ref = {p, 0, 0};
+    return intersect_compressed_host(ref, after_uid, v, m, out, out_cap, out_len);
+}
+extern "C" int dgx_intersect_compressed_ref(const dgx_pack_ref* ref, uint64_t after_uid, const uint64_t* v, size_t m,
+                                            uint64_t* out, size_t out_cap, size_t* out_len) {
+    if (!ref) return fail(DGX_ERR_ARG, "null ref");
+    return intersect_compressed_host(*ref, after_uid, v, m, out, out_cap, out_len);
 }
 
 // ---------------------------------------------------------------------------
@@ -1483,6 +1540,84 @@ extern "C" int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k, u
     else cudaStreamSynchronize(l->stream);  // nothing queued may outlive the references released below
     for (size_t i = 0; i < got; ++i) pack_release(pls[i]);
     return rc;
+}
+
+static int intersect_compressed_host(const dgx_pack_ref& ref, uint64_t after_uid, const uint64_t* v, size_t m,
+                                     uint64_t* out, size_t out_cap, size_t* out_len) {
+    if (out_len) *out_len = 0;
+    if (ref.pack == nullptr) return DGX_OK;  // `if pack == nil { return }` (algo/uidlist.go:34-36): o is left untouched
+    if (m >= (size_t(1) << 32)) {             // v-ranges are 32-bit: beyond that, decode from the seek and filter
+        const uint64_t* lists[1] = {v};
+        const size_t lens[1] = {m};
+        return dgx_decode_intersect_sorted(ref.pack, after_uid, lists, lens, 1, out, out_cap, out_len);
+    }
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    PackLease pl;
+    bool deferred = false;
+    int rc = pack_acquire(l, ref, &pl, &deferred);
+    if (rc == DGX_OK && deferred) rc = pack_upload_impl(l, ref.pack, nullptr, &l->ws, &pl.pk);
+    uint64_t* d_v = nullptr;
+    void *d_out = nullptr, *d_len = nullptr;
+    if (rc == DGX_OK) rc = upload_list(l, v, m, &d_v);
+    if (rc == DGX_OK) rc = l->ws.alloc((m + 2) * sizeof(uint64_t), &d_out);
+    if (rc == DGX_OK) rc = l->ws.alloc(64, &d_len);
+    if (rc == DGX_OK) rc = icw_impl(l, pl.pk, after_uid, d_v, m, (uint64_t*)d_out, m, (uint64_t*)d_len);
+    if (rc == DGX_OK) rc = finish_to_host(l, (uint64_t*)d_len, (uint64_t*)d_out, m, out, out_cap, out_len);
+    else cudaStreamSynchronize(l->stream);
+    pack_release(pl);
+    return rc;
+}
+
+// Decoder.Seek / SeekToBlock / LinearSeek / Next / UnpackBlock for one call (codec/codec.go:154-384), on the device.
+extern "C" int dgx_pack_seek(const dgx_pack_view* p, int kind, uint64_t uid, int whence, size_t block_idx,
+                             uint64_t* out, size_t out_cap, size_t* out_len, size_t* block_idx_after) {
+    if (out_len) *out_len = 0;
+    if (block_idx_after) *block_idx_after = 0;
+    if (!p || p->nblocks == 0) return DGX_OK;  // nil pack: every seek returns an empty slice
+    if (kind < SK_SEEK || kind > SK_UNPACK || (whence != 0 && whence != 1)) return fail(DGX_ERR_ARG, "bad seek kind / whence");
+    LaneLease lease;
+    if (lease.rc) return lease.rc;
+    dgx_lane* l = lease.l;
+    g_stats.calls += 1;
+    dgx_dev_pack pk;
+    int rc = pack_upload_impl(l, p, nullptr, &l->ws, &pk);
+    if (rc) return rc;
+    void *d_out, *d_meta;
+    const size_t cap = std::max<size_t>(pk.pk.max_num, 1);
+    rc = l->ws.alloc((cap + 2) * sizeof(uint64_t), &d_out);
+    if (rc) return rc;
+    rc = l->ws.alloc(64, &d_meta);
+    if (rc) return rc;
+    SeekParams S;
+    S.pk = pk.pk;
+    S.uid = uid;
+    S.whence = whence;
+    S.kind = kind;
+    S.block_idx = block_idx;
+    S.out = (u64*)d_out;
+    S.out_meta = (u64*)d_meta;
+    pack_seek_kernel<<<1, 32, 0, l->stream>>>(S);
+    CK(cudaGetLastError());
+    l->launches += 1;
+    g_stats.launches += 1;
+    CK(cudaMemcpyAsync(l->h_word, d_meta, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaMemcpyAsync(l->h_head, d_out, std::min(cap, kSpecHead) * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+    rc = dgx_lane_sync(l);
+    if (rc) return rc;
+    const uint64_t n = l->h_word[0];
+    if (block_idx_after) *block_idx_after = (size_t)l->h_word[1];
+    if (n > out_cap) return fail(DGX_ERR_CAP, "block (%llu uids) does not fit out_cap (%zu)", (unsigned long long)n, out_cap);
+    if (n > kSpecHead) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, l->stream));
+        CK(cudaStreamSynchronize(l->stream));
+    } else if (n) {
+        memcpy(out, l->h_head, n * sizeof(uint64_t));
+    }
+    if (out_len) *out_len = (size_t)n;
+    return DGX_OK;
 }
 
 // ---------------------------------------------------------------------------

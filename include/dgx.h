@@ -158,6 +158,22 @@ typedef struct dgx_pack_ref {
 int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k,
                                 uint64_t* out, size_t out_cap, size_t* out_len);
 
+/* algo.IntersectCompressedWith with a named (cacheable) pack; dgx_intersect_compressed is the anonymous form. */
+int dgx_intersect_compressed_ref(const dgx_pack_ref* ref, uint64_t after_uid, const uint64_t* v, size_t m,
+                                 uint64_t* out, size_t out_cap, size_t* out_len);
+
+/* codec.Decoder positioned calls (codec/codec.go:154-384), one call each, computed on the device:
+ *   kind 0 Decoder.Seek(uid, whence)          :279-337   whence 0 = SeekStart (>= uid), 1 = SeekCurrent (> uid)
+ *   kind 1 Decoder.SeekToBlock(uid, whence)   :219-271   resumes the base search at block_idx
+ *   kind 2 Decoder.LinearSeek(uid)            :349-359   advances from block_idx while uid >= next base
+ *   kind 3 Decoder.Next()                     :370-376
+ *   kind 4 Decoder.UnpackBlock()              :154-200   (block_idx itself)
+ * `block_idx` is the decoder's blockIdx before the call (its current block counts as fully unpacked); the
+ * returned slice is what the Go call returns, *block_idx_after the decoder's blockIdx afterwards.
+ * out_cap >= the pack's largest NumUids (BlockSize for packs built by codec.Encode). */
+int dgx_pack_seek(const dgx_pack_view* p, int kind, uint64_t uid, int whence, size_t block_idx,
+                  uint64_t* out, size_t out_cap, size_t* out_len, size_t* block_idx_after);
+
 typedef struct dgx_cache_stats {
     uint64_t hits, misses, evictions;
     uint64_t bytes, entries, max_bytes;

@@ -285,3 +285,125 @@ def test_config5_full(dgx, orc):
     d = gen.thin(np.random.default_rng(502), master, 0.05)
     got = dgx.algo.Difference(merged, L(dgx, d))
     same(got.Uids, orc.difference(want, d), "C5 Difference")
+
+
+# ---- Decoder seeks on the device (codec_test.go:113-217) ------------------------------------------------
+
+def test_device_seek_tables(dgx, orc):
+    from test_oracle_codec import SEEK_TABLE, make_seek_pack
+
+    opack = make_seek_pack(orc)
+    dec = dgx.codec.Decoder(to_pack(dgx, opack))
+    ref = orc.Decoder(opack)
+    # TestSeek :125-151 -- same table the oracle is pinned with, and the oracle's answer call by call
+    for uid, out, whence, empty in SEEK_TABLE:
+        uids = dec.Seek(uid, whence)
+        want = ref.seek(uid, whence)
+        eq(uids, want, f"Seek({uid},{whence})")
+        assert dec.BlockIdx() == ref.block_idx
+        if empty:
+            assert uids.size == 0
+        else:
+            assert int(uids[0]) == out
+    # :153-157
+    dec.blockIdx = 0
+    ref.block_idx = 0
+    for i in range(100, 10000, 100):
+        got = dec.LinearSeek(i)
+        eq(got, ref.linear_seek(i), f"LinearSeek({i})")
+        assert i in got.tolist()
+    # TestLinearSeek :160-187
+    dec = dgx.codec.Decoder(to_pack(dgx, opack))
+    ref = orc.Decoder(opack)
+    N = 10001
+    for i in range(0, 2 * N, 130):
+        got = dec.LinearSeek(i)
+        eq(got, ref.linear_seek(i), f"LinearSeek({i})")
+        assert (i in got.tolist()) == (i < N)
+        assert dec.BlockIdx() == ref.block_idx
+    for i in range(0, 9990, 370):   # blockIdx now points at the last block
+        assert i not in dec.LinearSeek(i).tolist()
+    # TestDecoder :190-217
+    expected = np.arange(3, N, 3, dtype=np.uint64)
+    p3 = orc.encode(expected, 10)
+    dec = dgx.codec.Decoder(to_pack(dgx, p3))
+    for i in range(3, N, 3 * 97):
+        for d in (0, 1, 2):
+            assert int(dec.Seek(i - d, dgx.codec.SeekStart)[0]) == i
+        assert int(dec.Seek(i, dgx.codec.SeekCurrent)[0]) == i + 3 if i + 3 < N else True
+    # SeekToBlock / LinearSeek / Next / UnpackBlock against the oracle, call by call, the block index carried over.
+    # (Seek is left out of the walk: it trims the current slice, and the reference's SeekToBlock reuses a trimmed
+    # slice when the block does not change, codec.go:262-264 -- state the one-call device form does not carry.)
+    dec = dgx.codec.Decoder(to_pack(dgx, opack))
+    ref = orc.Decoder(opack)
+    dec.UnpackBlock()
+    ref.unpack_block()
+    rng = np.random.default_rng(40)
+    for step in range(300):
+        kind = int(rng.integers(0, 4))
+        uid = int(rng.integers(0, 10400))
+        wh = int(rng.integers(0, 2))
+        if not ref.valid():
+            dec.blockIdx = ref.block_idx = 0
+            dec.UnpackBlock()
+            ref.unpack_block()
+        if kind == 0:
+            got, want = dec.SeekToBlock(uid, wh), ref.seek_to_block(uid, wh)
+        elif kind == 1:
+            got, want = dec.LinearSeek(uid), ref.linear_seek(uid)
+        elif kind == 2:
+            got, want = dec.Next(), ref.next()
+        else:
+            got, want = dec.UnpackBlock(), ref.unpack_block()
+        eq(got, want, f"step {step} kind {kind} uid {uid} whence {wh}")
+        assert dec.BlockIdx() == ref.block_idx, (step, kind, uid, wh)
+    # nil pack
+    d0 = dgx.codec.Decoder(None)
+    assert d0.Seek(5, 0).size == 0 and d0.LinearSeek(5).size == 0 and not d0.Valid()
+
+
+def test_intersect_compressed_fused(dgx, orc):
+    """The fused block-skipping kernel in both range-search regimes (m < nblocks: bases searched with v;
+    m >= nblocks: v searched with the bases), both probe directions, sparse and dense v, afterUID seeks,
+    non-reference block sizes (oversize slow path) and the named-pack form."""
+    import ctypes as C
+    from dgraph_b200 import _lib
+
+    rng = np.random.default_rng(41)
+    u = gen.zipf_gaps(rng, 2_000_000)
+    pack = orc.encode(u, 256)
+    p = to_pack(dgx, pack)
+    cases = [gen.thin(rng, u, 1e-4), gen.thin(rng, u, 0.02), gen.thin(rng, u, 0.9),
+             np.unique(np.concatenate([gen.thin(rng, u, 0.001), rng.integers(0, int(u[-1]) + 1000, 5000, dtype=np.uint64)])),
+             u.copy(), u[:1], u[-1:], np.array([0], np.uint64), np.array([int(u[-1]) + 1], np.uint64)]
+    dense = np.unique(np.concatenate([u[1000:200000], np.arange(int(u[1000]), int(u[1000]) + 3_000_000, 3, dtype=np.uint64)]))
+    cases.append(dense)   # slices of v far longer than a block: the row probes the slice
+    for ci, v in enumerate(cases):
+        for after in (0, int(u[u.size // 3]), int(u[u.size // 3]) + 1, int(u[-1]), int(u[-1]) + 1):
+            o = dgx.pb.List(None)
+            dgx.algo.IntersectCompressedWith(p, after, L(dgx, v), o)
+            eq(o.Uids, orc.intersect_compressed_with(pack, after, v), f"case {ci} after {after}")
+    for bs in (1, 7, 100, 1000, 5000):
+        w = gen.zipf_gaps(rng, 60_000)
+        pk = orc.encode(w, bs)
+        for v in (gen.thin(rng, w, 0.3), gen.thin(rng, w, 0.003)):
+            o = dgx.pb.List(None)
+            dgx.algo.IntersectCompressedWith(to_pack(dgx, pk), int(w[100]), L(dgx, v), o)
+            eq(o.Uids, orc.intersect_compressed_with(pk, int(w[100]), v), f"bs {bs}")
+    # named pack: second call hits the cache
+    lib = _lib.load()
+    lib.dgx_cache_clear()
+    v = gen.thin(rng, u, 0.01)
+    pn = p.normalized()
+    view = dgx.codec.view_of(pn)
+    ref = _lib.PackRef(C.pointer(view), 777, 3)
+    out = np.empty(v.size, np.uint64)
+    n = C.c_size_t(0)
+    st = _lib.CacheStats()
+    for rep in range(2):
+        _lib.check(lib.dgx_intersect_compressed_ref(C.byref(ref), 0, v.ctypes.data_as(C.c_void_p), v.size,
+                                                    out.ctypes.data_as(C.c_void_p), v.size, C.byref(n)))
+        eq(out[: n.value], orc.intersect_compressed_with(pack, 0, v), f"named rep {rep}")
+    lib.dgx_cache_get_stats(C.byref(st))
+    assert st.hits >= 1
+    lib.dgx_cache_clear()
