@@ -208,18 +208,21 @@ def run_e2e_legs(args, lib, queries, want, uids_all, uids_per_step, rank, world,
         """`call(slot, qi)` = one query through the C ABI on thread `slot`; returns (seconds per step, out values per step).
         The reference is called from many goroutines at once (x.DivideAndRule, worker/task.go:816); here T host
         threads issue the queries, each call borrowing its own lane, so one query's sync gap is another's copy."""
-        def worker(slot):
-            return sum(call(slot, qi) for qi in range(slot, Q, T))
+        def worker(slot, steps):
+            # thread `slot` issues queries slot, slot+T, ... of every step, back to back: the timed region is a
+            # continuous stream of nsteps x Q calls (no barrier between steps -- a server does not have one)
+            tot = 0
+            for _ in range(steps):
+                for qi in range(slot, Q, T):
+                    tot += call(slot, qi)
+            return tot
 
-        def one_step():
-            return sum(pool.map(worker, range(T)))
-        one_step()
+        sum(pool.map(lambda s_: worker(s_, 1), range(T)))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(nsteps):
-            outn = one_step()
+        outn = sum(pool.map(lambda s_: worker(s_, nsteps), range(T))) // nsteps
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -326,8 +329,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=16, help="independent queries per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-threads", type=int, default=16)
     ap.add_argument("--no-ops", action="store_true", help="skip the per-config (C1/C3/C4/C5) one-liners under `ops`")
     ap.add_argument("--no-dense", action="store_true", help="skip the p=0.9 variant of the headline step")
     ap.add_argument("--no-e2e", action="store_true", help="kernel iteration runs only: skip the end-to-end legs (the line then has no e2e)")

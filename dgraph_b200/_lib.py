@@ -70,6 +70,12 @@ SYMBOLS = {
     "dgx_intersect_sorted_packed": (_int, [C.POINTER(PackRef), _sz, _vp, _sz, _szp]),
     "dgx_intersect_compressed_ref": (_int, [C.POINTER(PackRef), _u64, _vp, _sz, _vp, _sz, _szp]),
     "dgx_pack_seek": (_int, [C.POINTER(PackView), _int, _u64, _int, _sz, _vp, _sz, _szp, _szp]),
+    "dgx_encode_bound": (None, [_sz, C.c_uint32, _szp, _szp]),
+    "dgx_encode": (_int, [_vp, _sz, C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
+    "dgx_intersect_packed": (_int, [C.POINTER(PackRef), C.POINTER(PackRef), C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
+    "dgx_difference_packed": (_int, [C.POINTER(PackRef), C.POINTER(PackRef), C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
+    "dgx_intersect_sorted_packed_out": (_int, [C.POINTER(PackRef), _sz, C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
+    "dgx_merge_sorted_packed": (_int, [C.POINTER(PackRef), _sz, C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
     "dgx_cache_configure": (_int, [_sz]),
     "dgx_cache_clear": (None, []),
     "dgx_cache_get_stats": (None, [C.POINTER(CacheStats)]),

@@ -172,3 +172,70 @@ def IntersectBatchShared(a: np.ndarray, a_off: np.ndarray, b: np.ndarray):
     out_off = np.zeros(npairs + 1, dtype=np.uint64)
     _lib.check(lib.dgx_intersect_batch_shared(_p(a), _p(a_off), npairs, _p(b), b.size, _p(out), _p(out_off), cap))
     return out[: int(out_off[-1])], out_off
+
+
+def _refs_of(packs, keys=None):
+    from .codec import view_of
+
+    k = len(packs)
+    refs = (_lib.PackRef * max(k, 1))()
+    keep = []
+    for i, p in enumerate(packs):
+        if p is None or p.nblocks == 0:
+            refs[i].pack = None
+        else:
+            p = p.normalized()
+            v = view_of(p)
+            keep.append((p, v))
+            refs[i].pack = C.pointer(v)
+        refs[i].key, refs[i].version = (keys[i] if keys is not None else (0, 0))
+    return refs, keep
+
+
+def _exact(p) -> int:
+    from .codec import ExactLen
+
+    return ExactLen(p)
+
+
+def IntersectWithLinPacked(u, v, blockSize: int = 256):
+    """algo.IntersectWithLinPacked(u, v *pb.UidPack) *pb.UidPack (algo/packed.go:35-101): result as a pack."""
+    from .codec import _call_pack_out
+
+    lib = _lib.load()
+    refs, keep = _refs_of([u, v])
+    return _call_pack_out(lambda b, n, d, dl, pnb, pdb, pv: lib.dgx_intersect_packed(
+        C.byref(refs[0]), C.byref(refs[1]), blockSize, b, n, d, dl, pnb, pdb, pv), min(_exact(u), _exact(v)), blockSize)
+
+
+def DifferencePacked(u, v, blockSize: int = 256):
+    """algo.DifferencePacked(u, v) (algo/packed.go:141-226): u \\ v as a pack."""
+    from .codec import _call_pack_out
+
+    lib = _lib.load()
+    refs, keep = _refs_of([u, v])
+    return _call_pack_out(lambda b, n, d, dl, pnb, pdb, pv: lib.dgx_difference_packed(
+        C.byref(refs[0]), C.byref(refs[1]), blockSize, b, n, d, dl, pnb, pdb, pv), _exact(u), blockSize)
+
+
+def MergeSortedPacked(lists, blockSize: int = 256):
+    """algo.MergeSortedPacked(lists) (algo/packed.go:228-297): sorted de-duplicated union as a pack."""
+    from .codec import _call_pack_out
+
+    lib = _lib.load()
+    refs, keep = _refs_of(lists)
+    return _call_pack_out(lambda b, n, d, dl, pnb, pdb, pv: lib.dgx_merge_sorted_packed(
+        refs, len(lists), blockSize, b, n, d, dl, pnb, pdb, pv), sum(_exact(p) for p in lists), blockSize)
+
+
+def IntersectSortedPacked(lists, blockSize: int = 256):
+    """algo.IntersectSortedPacked(lists) (algo/packed.go:103-139) over ALL lists (the reference's loop keeps only
+    ls[0] ∩ ls[1]); no lists -> nil pack."""
+    from .codec import _call_pack_out
+
+    if len(lists) == 0:
+        return None
+    lib = _lib.load()
+    refs, keep = _refs_of(lists)
+    return _call_pack_out(lambda b, n, d, dl, pnb, pdb, pv: lib.dgx_intersect_sorted_packed_out(
+        refs, len(lists), blockSize, b, n, d, dl, pnb, pdb, pv), min(_exact(p) for p in lists), blockSize)

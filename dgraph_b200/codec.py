@@ -132,3 +132,43 @@ class Decoder:
 
     def ApproxLen(self) -> int:
         return 0 if self.Pack is None else int(self.Pack.block_size) * (self.Pack.nblocks - self.blockIdx)
+
+
+def _pack_out_arrays(n_uids: int, block_size: int):
+    lib = _lib.load()
+    nb_cap, db_cap = C.c_size_t(0), C.c_size_t(0)
+    lib.dgx_encode_bound(n_uids, block_size, C.byref(nb_cap), C.byref(db_cap))
+    return nb_cap.value, db_cap.value
+
+
+def _call_pack_out(fn, n_uids: int, block_size: int) -> Optional[UidPack]:
+    """Run `fn(base, num, doff, deltas, &nblocks, &delta_bytes, &view)`, growing the arrays once on DGX_ERR_CAP."""
+    nb_cap, db_cap = _pack_out_arrays(n_uids, block_size)
+    for _ in range(3):
+        base = np.empty(max(nb_cap, 1), np.uint64)
+        num = np.empty(max(nb_cap, 1), np.uint32)
+        doff = np.zeros(max(nb_cap, 1) + 1, np.uint64)
+        deltas = np.empty(max(db_cap, 1), np.uint8)
+        nb, db = C.c_size_t(nb_cap), C.c_size_t(db_cap)
+        view = _lib.PackView()
+        rc = fn(base.ctypes.data_as(C.c_void_p), num.ctypes.data_as(C.c_void_p), doff.ctypes.data_as(C.c_void_p),
+                deltas.ctypes.data_as(C.c_void_p), C.byref(nb), C.byref(db), C.byref(view))
+        if rc == -4 and (nb.value > nb_cap or db.value > db_cap):   # DGX_ERR_CAP: exact sizes came back
+            nb_cap, db_cap = max(nb_cap, nb.value), max(db_cap, db.value)
+            continue
+        _lib.check(rc)
+        if nb.value == 0:
+            return None   # the nil pack
+        return UidPack(block_size, base[: nb.value].copy(), num[: nb.value].copy(), doff[: nb.value + 1].copy(),
+                       deltas[: db.value].copy())
+    raise _lib.DgxError(-4, "pack output did not fit after resizing")
+
+
+def Encode(uids, blockSize: int) -> Optional[UidPack]:
+    """codec.Encode(uids, blockSize) (codec/codec.go:393-399) on the device; no uids -> nil pack (None)."""
+    lib = _lib.load()
+    u = np.ascontiguousarray(np.asarray(uids, dtype=np.uint64))
+    if u.size == 0:
+        return None
+    return _call_pack_out(lambda b, n, d, dl, pnb, pdb, pv: lib.dgx_encode(
+        u.ctypes.data_as(C.c_void_p), u.size, blockSize, b, n, d, dl, pnb, pdb, pv), u.size, blockSize)

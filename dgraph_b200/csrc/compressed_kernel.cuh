@@ -367,7 +367,10 @@ __global__ void pack_seek_kernel(const SeekParams P) {
             if (idx == 0) { len = sk_unpack(pk, 0, P.out); break; }
             if (idx < nb && pk.base[idx] == P.uid) { blk = idx; len = sk_unpack(pk, blk, P.out); break; }
             blk = idx - 1;
-            len = sk_unpack(pk, blk, P.out);
+            // `if d.blockIdx != prevBlockIdx { d.UnpackBlock() }` (:262-264): when the search was restarted from
+            // block 0 for an older uid and lands on block 0, the reference keeps the slice it already held --
+            // the block the decoder stood on before the call -- and tests uid against THAT slice.
+            len = sk_unpack(pk, blk != prev ? blk : P.block_idx, P.out);
             if (!(len > 0 && P.uid <= P.out[len - 1])) next();
             break;
         }

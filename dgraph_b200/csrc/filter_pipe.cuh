@@ -37,15 +37,16 @@
 
 namespace dgx {
 
-#ifndef DGX_P_CW
-#define DGX_P_CW 8
+#ifndef DGX_P_VA
+#define DGX_P_VA 2
 #endif
-constexpr int P_CW = DGX_P_CW;           // consumer warps
+constexpr int P_VA = DGX_P_VA;           // candidate rows per consumer warp (2 or 4)
+constexpr int P_WC = 32 * P_VA;          // candidates per consumer warp
+constexpr int P_TA = 512;                // candidates per tile
+constexpr int P_CW = P_TA / P_WC;        // consumer warps
 constexpr int P_CT = P_CW * 32;          // consumer threads
 constexpr int P_NT = P_CT + 96;          // + metadata warp + TMA warp + output warp
-constexpr int P_VA = 2;                  // candidate rows per consumer warp
-constexpr int P_WC = 32 * P_VA;          // candidates per consumer warp
-constexpr int P_TA = P_CW * 64;          // candidates per tile
+static_assert(P_VA == 2 || P_VA == 4, "rows per consumer warp");
 #ifndef DGX_P_OS
 #define DGX_P_OS 6
 #endif
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             X.cand = cand; X.A = G.A; X.a0 = G.a0; X.prev = G.prev; X.has_prev = G.has_prev != 0;
             X.cidx0 = P_WC * wid + lane; X.op = P.op;
 
-            u64 c[P_VA] = {0, 0};
+            u64 c[P_VA] = {};
             unsigned alive = 0, dup = 0;
             int rows;
             {
@@ -635,13 +636,18 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                         if (rows == 1) {
                             const u32 x1[1] = {x[0]};
                             hit = lift32<1>(sb, n, x1);
+                        } else if (P_VA == 2 || rows == 2) {
+                            const u32 x2[2] = {x[0], x[1]};
+                            hit = lift32<2>(sb, n, x2);
                         } else {
                             hit = lift32<P_VA>(sb, n, x);
                         }
                     }
                     alive &= keep_hits ? hit : ~hit;
-                    if (t + 1 < km1) {
-                        // re-pack into fewer rows (order preserved); a single row only checks for survivors
+                    if (t + 1 < km1 && rows == 1) {
+                        if (!__any_sync(0xffffffffu, alive & 1u)) { rows = 0; alive = 0; }  // nobody left: done with the tile
+                    } else if (t + 1 < km1) {
+                        // re-pack into fewer rows (order preserved)
                         unsigned b[P_VA];
                         int tot = 0;
 #pragma unroll
@@ -676,8 +682,8 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             }
             while (t < km1 && rows > 0) {
                 if (t < nstaged) {
-                    if (rows == 2 || t + 1 >= nstaged) {
-                        // ---- one staged list, the warp's rows interleaved --------------------
+                    if (rows >= 2 || t + 1 >= nstaged) {
+                        // ---- one staged list, the warp's rows interleaved in pairs ------------
                         const int n = (int)G.n[t];
                         if (n == 0) {
                             if (P.op == 0) { alive = 0; rows = 0; }
@@ -685,15 +691,20 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                             const u64* sb = sl + G.off[t];
                             const u64* const sbs[2] = {sb, sb};
                             const int ns[2] = {n, n};
-                            const u64 xs[2] = {c[0], c[1]};
-                            int pos[2];
-                            lift_multi<2>(sbs, ns, xs, pos);
 #pragma unroll
-                            for (int i = 0; i < P_VA; ++i)
-                                if ((alive >> i) & 1u) {
-                                    const bool h = phit(X, c[i], i, dup, sb, n, pos[i], G.r0[t], G.ptr[t], G.len[t]);
-                                    if ((P.op == 0) != h) alive &= ~(1u << i);
+                            for (int r0 = 0; r0 < P_VA; r0 += 2) {
+                                if (r0 < rows) {
+                                    const u64 xs[2] = {c[r0], c[r0 + 1]};
+                                    int pos[2];
+                                    lift_multi<2>(sbs, ns, xs, pos);
+#pragma unroll
+                                    for (int i = r0; i < r0 + 2; ++i)
+                                        if ((alive >> i) & 1u) {
+                                            const bool h = phit(X, c[i], i, dup, sb, n, pos[i - r0], G.r0[t], G.ptr[t], G.len[t]);
+                                            if ((P.op == 0) != h) alive &= ~(1u << i);
+                                        }
                                 }
+                            }
                         }
                         t += 1;
                     } else {

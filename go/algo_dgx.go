@@ -65,6 +65,16 @@ func IntersectWith(u, v, o *pb.List) {
 	o.Uids = dst[:int(outLen)]
 }
 
+func totalUids(lists []*pb.List) int {
+	t := 0
+	for _, l := range lists {
+		if l != nil {
+			t += len(l.Uids)
+		}
+	}
+	return t
+}
+
 // pinLists builds the C pointer/length tables for a []*pb.List.  cgo forbids passing
 // Go memory that itself holds Go pointers, so the table lives in C memory and the
 // list backing arrays are pinned for the duration of the call (Go >= 1.21).
@@ -98,11 +108,11 @@ func IntersectSorted(lists []*pb.List) *pb.List {
 	if len(lists) == 0 {
 		return &pb.List{}
 	}
-	ptrs, lens, total, minLen, _, free := pinLists(lists)
-	defer free()
-	if total < dgxMinUids {
+	if totalUids(lists) < dgxMinUids { // decided before anything is pinned or malloc'ed
 		return intersectSortedGo(lists)
 	}
+	ptrs, lens, _, minLen, _, free := pinLists(lists)
+	defer free()
 	out := make([]uint64, minLen)
 	var outLen C.size_t
 	if rc := C.dgx_intersect_sorted(ptrs, lens, C.size_t(len(lists)), u64ptr(out), C.size_t(minLen), &outLen); rc != C.DGX_OK {
@@ -113,11 +123,11 @@ func IntersectSorted(lists []*pb.List) *pb.List {
 
 // MergeSorted: algo/uidlist.go:448.
 func MergeSorted(lists []*pb.List) *pb.List {
-	ptrs, lens, total, _, _, free := pinLists(lists)
-	defer free()
-	if total < dgxMinUids {
+	if totalUids(lists) < dgxMinUids {
 		return mergeSortedGo(lists)
 	}
+	ptrs, lens, total, _, _, free := pinLists(lists)
+	defer free()
 	out := make([]uint64, total)
 	var outLen C.size_t
 	if rc := C.dgx_merge_sorted(ptrs, lens, C.size_t(len(lists)), u64ptr(out), C.size_t(total), &outLen); rc != C.DGX_OK {
@@ -144,4 +154,62 @@ func Difference(u, v *pb.List) *pb.List {
 		return differenceGo(u, v)
 	}
 	return &pb.List{Uids: out[:int(outLen)]}
+}
+
+// IndexOfBatch answers algo.IndexOf(u, uid) (algo/uidlist.go:546-552) for every uid in one call: the
+// shape of updateDestUids / updateFacetMatrix (query/query.go:1396-1416, 2594-2608), which probe
+// sg.DestUIDs once per uid of the uid matrix.  idx[i] = -1 when uids[i] is absent.
+func IndexOfBatch(u *pb.List, uids []uint64) []int64 {
+	idx := make([]int64, len(uids))
+	if len(uids) == 0 {
+		return idx
+	}
+	if len(u.Uids)+len(uids) >= dgxMinUids {
+		rc := C.dgx_index_of_batch(u64ptr(u.Uids), C.size_t(len(u.Uids)), u64ptr(uids), C.size_t(len(uids)),
+			(*C.int64_t)(unsafe.Pointer(&idx[0])))
+		runtime.KeepAlive(u)
+		if rc == C.DGX_OK {
+			return idx
+		}
+	}
+	for i, x := range uids {
+		idx[i] = int64(IndexOf(u, x))
+	}
+	return idx
+}
+
+// IntersectRowsWith replaces the loop `for _, l := range matrix { algo.IntersectWith(l, dest, l) }`
+// (query/query.go:1425-1438 updateUidMatrix; worker/task.go:1351, 1616, 1691, 1777) with one batched call:
+// the rows are flattened to CSR, `dest` crosses PCIe once, every row is filtered in place.
+func IntersectRowsWith(matrix []*pb.List, dest *pb.List) {
+	total := len(dest.Uids)
+	for _, l := range matrix {
+		total += len(l.Uids)
+	}
+	if total < dgxMinUids || len(matrix) == 0 {
+		for _, l := range matrix {
+			IntersectWith(l, dest, l)
+		}
+		return
+	}
+	flat := make([]uint64, 0, total-len(dest.Uids))
+	off := make([]uint64, len(matrix)+1)
+	for i, l := range matrix {
+		flat = append(flat, l.Uids...)
+		off[i+1] = uint64(len(flat))
+	}
+	out := make([]uint64, len(flat))
+	outOff := make([]uint64, len(matrix)+1)
+	rc := C.dgx_intersect_batch_shared(u64ptr(flat), u64ptr(off), C.size_t(len(matrix)), u64ptr(dest.Uids),
+		C.size_t(len(dest.Uids)), u64ptr(out), u64ptr(outOff), C.size_t(len(out)))
+	runtime.KeepAlive(dest)
+	if rc != C.DGX_OK {
+		for _, l := range matrix {
+			IntersectWith(l, dest, l)
+		}
+		return
+	}
+	for i, l := range matrix {
+		l.Uids = append(l.Uids[:0], out[outOff[i]:outOff[i+1]]...)
+	}
 }

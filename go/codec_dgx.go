@@ -123,3 +123,113 @@ func DecodeStored(value []byte, seek uint64) ([]uint64, bool) {
 	}
 	return out[:int(outLen)], true
 }
+
+// packRef names a pack for the HBM-resident cache of libdgx: key = hash of the posting list's Badger key,
+// version = commit timestamp of the immutable layer the pack was rolled up at (posting.List.minTs).
+// key 0 = anonymous (copied for this call only).
+type PackRef struct {
+	Pack    *pb.UidPack
+	Key     uint64
+	Version uint64
+}
+
+// IntersectCompressedWithRef is algo.IntersectCompressedWith (algo/uidlist.go:33-61), the entry point of
+// posting.List.Uids for filtered reads (posting/list.go:1795-1800): o.Uids = v ∩ pack[>= afterUID].  The pack
+// crosses PCIe compressed (or not at all when (Key, Version) is already resident); only blocks whose range
+// holds an element of v are decoded.  Returns false when the caller must run the Go path.
+func IntersectCompressedWithRef(ref PackRef, afterUID uint64, v, o *pb.List) bool {
+	if ref.Pack == nil {
+		return true // `if pack == nil { return }`: o untouched
+	}
+	if ApproxLen(ref.Pack)+len(v.Uids) < dgxMinDecode {
+		return false
+	}
+	view, free := flatten(ref.Pack)
+	defer free()
+	cref := C.dgx_pack_ref{pack: &view, key: C.uint64_t(ref.Key), version: C.uint64_t(ref.Version)}
+	out := make([]uint64, len(v.Uids))
+	var outLen C.size_t
+	var vp, op *C.uint64_t
+	if len(v.Uids) > 0 {
+		vp = (*C.uint64_t)(unsafe.Pointer(&v.Uids[0]))
+		op = (*C.uint64_t)(unsafe.Pointer(&out[0]))
+	}
+	if C.dgx_intersect_compressed_ref(&cref, C.uint64_t(afterUID), vp, C.size_t(len(v.Uids)), op, C.size_t(len(out)), &outLen) != C.DGX_OK {
+		return false
+	}
+	o.Uids = out[:int(outLen)]
+	return true
+}
+
+// IntersectSortedPacks is algo.IntersectSorted over lists still held as packs: every pack is decoded on the
+// device (codec.Decode(p, 0)) and the k-way intersection runs there; ~1.5 B/UID cross PCIe instead of 8.
+func IntersectSortedPacks(refs []PackRef) (*pb.List, bool) {
+	if len(refs) == 0 {
+		return &pb.List{}, true
+	}
+	crefs := (*[1 << 20]C.dgx_pack_ref)(C.malloc(C.size_t(len(refs)) * C.size_t(unsafe.Sizeof(C.dgx_pack_ref{}))))
+	views := (*[1 << 20]C.dgx_pack_view)(C.malloc(C.size_t(len(refs)) * C.size_t(unsafe.Sizeof(C.dgx_pack_view{}))))
+	frees := make([]func(), 0, len(refs))
+	defer func() {
+		for _, f := range frees {
+			f()
+		}
+		C.free(unsafe.Pointer(crefs))
+		C.free(unsafe.Pointer(views))
+	}()
+	minLen := int(^uint(0) >> 1)
+	for i, r := range refs {
+		crefs[i] = C.dgx_pack_ref{key: C.uint64_t(r.Key), version: C.uint64_t(r.Version)}
+		if r.Pack == nil || len(r.Pack.Blocks) == 0 {
+			return &pb.List{Uids: []uint64{}}, true // an empty operand empties the intersection
+		}
+		v, free := flatten(r.Pack)
+		frees = append(frees, free)
+		views[i] = v
+		crefs[i].pack = &views[i]
+		if n := ExactLen(r.Pack); n < minLen {
+			minLen = n
+		}
+	}
+	out := make([]uint64, minLen+1)
+	var outLen C.size_t
+	if C.dgx_intersect_sorted_packed(&crefs[0], C.size_t(len(refs)), (*C.uint64_t)(unsafe.Pointer(&out[0])), C.size_t(minLen), &outLen) != C.DGX_OK {
+		return nil, false
+	}
+	return &pb.List{Uids: out[:int(outLen)]}, true
+}
+
+// EncodeDevice is codec.Encode (codec/codec.go:393-399) with the block split and the group-varint bytes produced
+// on the device; the result is rebuilt as a pb.UidPack whose blocks share one Deltas backing array.
+func EncodeDevice(uids []uint64, blockSize int) (*pb.UidPack, bool) {
+	if len(uids) == 0 {
+		return nil, true
+	}
+	var nbCap, dbCap C.size_t
+	C.dgx_encode_bound(C.size_t(len(uids)), C.uint32_t(blockSize), &nbCap, &dbCap)
+	for attempt := 0; attempt < 2; attempt++ {
+		base := make([]uint64, int(nbCap)+1)
+		num := make([]uint32, int(nbCap)+1)
+		off := make([]uint64, int(nbCap)+2)
+		del := make([]byte, int(dbCap)+1)
+		nb, db := nbCap, dbCap
+		rc := C.dgx_encode((*C.uint64_t)(unsafe.Pointer(&uids[0])), C.size_t(len(uids)), C.uint32_t(blockSize),
+			(*C.uint64_t)(unsafe.Pointer(&base[0])), (*C.uint32_t)(unsafe.Pointer(&num[0])),
+			(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint8_t)(unsafe.Pointer(&del[0])), &nb, &db, nil)
+		if rc == C.DGX_ERR_CAP && (nb > nbCap || db > dbCap) {
+			nbCap, dbCap = nb, db // the exact sizes came back: one more try
+			continue
+		}
+		if rc != C.DGX_OK {
+			return nil, false
+		}
+		pack := &pb.UidPack{BlockSize: uint32(blockSize), Blocks: make([]*pb.UidBlock, int(nb))}
+		blocks := make([]pb.UidBlock, int(nb))
+		for i := range blocks {
+			blocks[i] = pb.UidBlock{Base: base[i], NumUids: num[i], Deltas: del[off[i]:off[i+1]:off[i+1]]}
+			pack.Blocks[i] = &blocks[i]
+		}
+		return pack, true
+	}
+	return nil, false
+}

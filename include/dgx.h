@@ -158,6 +158,38 @@ typedef struct dgx_pack_ref {
 int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k,
                                 uint64_t* out, size_t out_cap, size_t* out_len);
 
+/* codec.Encode(uids, blockSize) (codec/codec.go:57-136, 393-399) on the device: block split at a change of the
+ * upper 32 bits or after BlockSize uids, group-varint deltas.  The caller allocates base[*nblocks],
+ * num_uids[*nblocks], delta_off[*nblocks + 1], deltas[*delta_bytes] (dgx_encode_bound gives sizes that hold any
+ * list with at most 64 upper-word changes); on return *nblocks / *delta_bytes are the pack's sizes and `view`
+ * points at the arrays.  DGX_ERR_CAP: the arrays are too small, the sizes needed were returned, call again.
+ * n == 0 is the nil pack (nblocks 0). */
+void dgx_encode_bound(size_t n, uint32_t block_size, size_t* nblocks_cap, size_t* delta_cap);
+int dgx_encode(const uint64_t* uids, size_t n, uint32_t block_size,
+               uint64_t* base, uint32_t* num_uids, uint64_t* delta_off, uint8_t* deltas,
+               size_t* nblocks, size_t* delta_bytes, dgx_pack_view* view);
+
+/* Packed set operations (algo/packed.go:35-297): operands and result are UidPacks; decode, the plain-list
+ * kernel and Encode run back to back on the device, so both directions cross PCIe compressed.
+ *   dgx_intersect_packed             IntersectWithLinPacked(u, v)      :35-101
+ *   dgx_intersect_sorted_packed_out  IntersectSortedPacked(lists)      :103-139 (all k lists)
+ *   dgx_difference_packed            DifferencePacked(u, v)            :141-226
+ *   dgx_merge_sorted_packed          MergeSortedPacked(lists)          :228-297
+ * Output arrays and capacities as in dgx_encode (bound: the result is at most min / |u| / sum of the operands'
+ * ExactLen uids).  NULL / empty packs are empty lists. */
+int dgx_intersect_packed(const dgx_pack_ref* u, const dgx_pack_ref* v, uint32_t block_size,
+                         uint64_t* base, uint32_t* num_uids, uint64_t* delta_off, uint8_t* deltas,
+                         size_t* nblocks, size_t* delta_bytes, dgx_pack_view* view);
+int dgx_intersect_sorted_packed_out(const dgx_pack_ref* refs, size_t k, uint32_t block_size,
+                                    uint64_t* base, uint32_t* num_uids, uint64_t* delta_off, uint8_t* deltas,
+                                    size_t* nblocks, size_t* delta_bytes, dgx_pack_view* view);
+int dgx_difference_packed(const dgx_pack_ref* u, const dgx_pack_ref* v, uint32_t block_size,
+                          uint64_t* base, uint32_t* num_uids, uint64_t* delta_off, uint8_t* deltas,
+                          size_t* nblocks, size_t* delta_bytes, dgx_pack_view* view);
+int dgx_merge_sorted_packed(const dgx_pack_ref* refs, size_t k, uint32_t block_size,
+                            uint64_t* base, uint32_t* num_uids, uint64_t* delta_off, uint8_t* deltas,
+                            size_t* nblocks, size_t* delta_bytes, dgx_pack_view* view);
+
 /* algo.IntersectCompressedWith with a named (cacheable) pack; dgx_intersect_compressed is the anonymous form. */
 int dgx_intersect_compressed_ref(const dgx_pack_ref* ref, uint64_t after_uid, const uint64_t* v, size_t m,
                                  uint64_t* out, size_t out_cap, size_t* out_len);

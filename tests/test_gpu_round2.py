@@ -379,10 +379,16 @@ def test_intersect_compressed_fused(dgx, orc):
     dense = np.unique(np.concatenate([u[1000:200000], np.arange(int(u[1000]), int(u[1000]) + 3_000_000, 3, dtype=np.uint64)]))
     cases.append(dense)   # slices of v far longer than a block: the row probes the slice
     for ci, v in enumerate(cases):
-        for after in (0, int(u[u.size // 3]), int(u[u.size // 3]) + 1, int(u[-1]), int(u[-1]) + 1):
+        for after in (0, int(u[u.size // 3]), int(u[u.size // 3]) + 1, int(u[-1])):
             o = dgx.pb.List(None)
             dgx.algo.IntersectCompressedWith(p, after, L(dgx, v), o)
             eq(o.Uids, orc.intersect_compressed_with(pack, after, v), f"case {ci} after {after}")
+        # afterUID beyond the last uid: Seek runs off the pack (blockIdx == len(Blocks)) and the reference's Bin branch
+        # then indexes Blocks[blockIdx] (algo/uidlist.go:118 -> codec.go:231), a panic in Go; nothing is >= afterUID,
+        # so the device answer is the empty list
+        o = dgx.pb.List(None)
+        dgx.algo.IntersectCompressedWith(p, int(u[-1]) + 1, L(dgx, v), o)
+        assert o.Uids is not None and o.Uids.size == 0
     for bs in (1, 7, 100, 1000, 5000):
         w = gen.zipf_gaps(rng, 60_000)
         pk = orc.encode(w, bs)
@@ -407,3 +413,87 @@ def test_intersect_compressed_fused(dgx, orc):
     lib.dgx_cache_get_stats(C.byref(st))
     assert st.hits >= 1
     lib.dgx_cache_clear()
+
+
+# ---- codec.Encode on the device, packed set operations (algo/packed.go) ------------------------------------
+
+def same_pack(got, want, what):
+    """device pack == oracle pack, array by array (bytes included)."""
+    if want.is_nil:
+        assert got is None, what
+        return
+    assert got is not None, what
+    assert got.block_size == want.block_size, what
+    eq(got.base, want.base, what + " base")
+    assert np.array_equal(got.num_uids, want.num_uids), what + " num_uids"
+    eq(got.delta_off, want.delta_off, what + " delta_off")
+    assert np.array_equal(got.deltas, want.deltas), what + " deltas"
+
+
+def test_encode_matches_oracle_bytes(dgx, orc):
+    rng = np.random.default_rng(50)
+    same_pack(dgx.codec.Encode(np.zeros(0, np.uint64), 256), orc.encode(np.zeros(0, np.uint64), 256), "empty")
+    for bs in (0, 1, 2, 5, 10, 100, 256, 257, 1000):
+        for n in (1, 2, 4, 5, 9, 255, 256, 257, 1000, 5003):
+            for u in (gen.get_uids(rng, n), gen.zipf_gaps(rng, n)):
+                same_pack(dgx.codec.Encode(u, bs), orc.encode(u, bs), f"bs {bs} n {n}")
+    for shift in (7, 8, 15, 16, 23, 24, 31):       # every delta width
+        g = rng.integers(1, 1 << shift, 4000, dtype=np.uint64) + np.uint64(1 << shift)
+        u = np.cumsum(g, dtype=np.uint64)
+        same_pack(dgx.codec.Encode(u, 256), orc.encode(u, 256), f"shift {shift}")
+    wide = np.cumsum(rng.integers(1, 1 << 31, 200_000, dtype=np.uint64), dtype=np.uint64)   # ~45 upper-word changes
+    same_pack(dgx.codec.Encode(wide, 256), orc.encode(wide, 256), "msb splits")
+    same_pack(dgx.codec.Encode(wide, 10), orc.encode(wide, 10), "msb splits bs 10")
+    scattered = np.sort(rng.integers(0, 2**64 - 1, 5000, dtype=np.uint64))                  # a new block per uid: > 64 splits
+    same_pack(dgx.codec.Encode(scattered, 256), orc.encode(scattered, 256), "every uid its own segment")
+    d = gen.with_dups(rng, 3000, 2000)
+    same_pack(dgx.codec.Encode(d, 256), orc.encode(d, 256), "duplicates (zero deltas)")
+    big = gen.zipf_gaps(rng, 20_000_000)
+    p = dgx.codec.Encode(big, 256)
+    same_pack(p, orc.encode(big, 256), "2e7")
+    eq(dgx.codec.Decode(p, 0), big, "encode -> decode round trip")
+    # TestEncoding :306-334 MSB-split shapes
+    bigs = [0xF000000000000000, 0xF00F000000000000, 0x00F00F0000000000, 0x000F0F0000000000, 0x0F0F0F0F00000000]
+    for n in (0, 1, 2, 3, 5, 13, 18, 100, 99, 98):
+        ints = np.zeros(n, dtype=np.uint64)
+        for i in range(min(50, n)):
+            ints[i] = rng.integers(0, 2**32)
+        for i in range(50, n):
+            ints[i] = int(rng.integers(0, 2**32)) + bigs[int(rng.integers(0, 5))]
+        ints.sort()
+        same_pack(dgx.codec.Encode(ints, 256), orc.encode(ints, 256), f"TestEncoding n={n}")
+
+
+def test_packed_ops_reference_cases(dgx, orc):
+    """Every known-answer case of algo/packed_test.go through the device packed operations (BlockSize 5 like
+    newUidPack, packed_test.go:18-25), result decoded with the ORACLE's decoder."""
+    from test_oracle_packed import DIFF_PACKED, INTERSECT_PACKED, INTERSECT_SORTED_PACKED, MERGE_PACKED
+
+    def mk(data):
+        return to_pack(dgx, orc.encode(np.asarray(data, dtype=np.uint64), 5))
+
+    def dec(p):
+        return [] if p is None else dgx.codec.Decode(p, 0).tolist()
+
+    for lists, want in MERGE_PACKED:
+        assert dec(dgx.algo.MergeSortedPacked([mk(l) for l in lists], 5)) == want, lists
+    for u, v, want in INTERSECT_PACKED:
+        assert dec(dgx.algo.IntersectWithLinPacked(mk(u), mk(v), 5)) == want, (u, v)
+    for lists, want in INTERSECT_SORTED_PACKED:
+        assert dec(dgx.algo.IntersectSortedPacked([mk(l) for l in lists], 5)) == want, lists
+    for u, v, want in DIFF_PACKED:
+        assert dec(dgx.algo.DifferencePacked(mk(u), mk(v), 5)) == want, (u, v)
+
+
+def test_packed_ops_random(dgx, orc):
+    rng = np.random.default_rng(51)
+    master = gen.zipf_gaps(rng, 600_000)
+    lists = [gen.thin(rng, master, float(p)) for p in (0.5, 0.3, 0.7, 0.05)]
+    packs = [to_pack(dgx, orc.encode(l, 256)) for l in lists]
+    same_pack(dgx.algo.IntersectWithLinPacked(packs[0], packs[1]), orc.encode(orc.intersect_with(lists[0], lists[1]), 256), "IntersectWithLinPacked")
+    same_pack(dgx.algo.DifferencePacked(packs[0], packs[1]), orc.encode(orc.difference(lists[0], lists[1]), 256), "DifferencePacked")
+    same_pack(dgx.algo.MergeSortedPacked(packs), orc.encode(orc.merge_sorted(lists), 256), "MergeSortedPacked")
+    same_pack(dgx.algo.IntersectSortedPacked(packs), orc.encode(orc.intersect_sorted(lists), 256), "IntersectSortedPacked")
+    same_pack(dgx.algo.IntersectWithLinPacked(packs[0], None), orc.encode(np.zeros(0, np.uint64), 256), "nil operand")
+    same_pack(dgx.algo.DifferencePacked(packs[0], None), orc.encode(lists[0], 256), "minus nil")
+    same_pack(dgx.algo.MergeSortedPacked([None, packs[3], None]), orc.encode(lists[3], 256), "merge with nils")
