@@ -119,7 +119,7 @@ def IntersectBatch(a: np.ndarray, a_off: np.ndarray, b: np.ndarray, b_off: np.nd
     return out[: int(out_off[-1])], out_off
 
 
-def IntersectSortedPacked(packs, keys=None) -> List:
+def IntersectSortedPacks(packs, keys=None) -> List:
     """algo.IntersectSorted over lists held as UidPacks (dgx_intersect_sorted_packed): the packs cross
     PCIe compressed and are decoded on the device (codec.Decode(p, 0) for each, codec/codec.go:444).
 

@@ -295,27 +295,42 @@ __device__ __forceinline__ u32 lds32r(u32 addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// R rows of one lane against the slice at shared byte address sb (n >= 1 values, 8-byte stride).
-// Returns bit i set when x[i] is present.
-template <int R>
-__device__ __forceinline__ unsigned lift32(u32 sb, u32 n, const u32 (&x)[R]) {
-    const int l2 = 31 - __clz(n);
-    const u32 p2 = 1u << l2;
-    u32 a[R];
-    {
-        const u32 pivot = lds32r(sb + (p2 - 1u) * 8u);
-        const u32 hi_window = sb + (n - p2) * 8u;
+// R rows of one lane against NL staged slices at once (slice j: shared byte address sb[j], n[j] >= P values at an
+// 8-byte stride), every (row, list) pair an independent dependency chain.  All chains run the SAME ladder: a window
+// of P = 2^l2P values per slice, P <= n[j] <= 3P.  The window is chosen by three pivots -- the last elements of
+// windows starting at 0, s1, s2 (s1 = ceil((n-P)/3), s2 = 2 s1, both clamped to n-P); a fourth window ends the
+// slice.  Neighbouring windows touch or overlap (s1 <= P), so the lower bound of x lies in the first window whose
+// last element is >= x, or nowhere.  hit[j] bit i = x[i] is present in slice j.
+template <int R, int NL>
+__device__ __forceinline__ void lift32m(const u32 (&sb)[NL], const u32 (&n)[NL], int l2P, const u32 (&x)[R],
+                                        unsigned (&hit)[NL]) {
+    const u32 Pw = 1u << l2P;
+    u32 a[NL][R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) a[i] = pivot < x[i] ? hi_window : sb;
+    for (int j = 0; j < NL; ++j) {
+        const u32 y = n[j] - Pw;
+        const u32 d = (y + 2u) / 3u;
+        const u32 s1 = d < y ? d : y, s2 = 2u * d < y ? 2u * d : y;
+        const u32 e0 = sb[j] + (Pw - 1u) * 8u;
+        const u32 p0 = lds32r(e0), p1 = lds32r(e0 + s1 * 8u), p2 = lds32r(e0 + s2 * 8u);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            u32 st = sb[j];
+            if (p0 < x[i]) st = sb[j] + s1 * 8u;
+            if (p1 < x[i]) st = sb[j] + s2 * 8u;
+            if (p2 < x[i]) st = sb[j] + y * 8u;
+            a[j][i] = st;
+        }
     }
-#define DGX_L32(H)                                                      \
-    {                                                                   \
-        _Pragma("unroll") for (int i = 0; i < R; ++i) {                 \
-            const u32 v_ = lds32<((H) - 1) * 8>(a[i]);                  \
-            if (v_ < x[i]) a[i] += (H) * 8;                             \
-        }                                                               \
+#define DGX_L32(H)                                                          \
+    {                                                                       \
+        _Pragma("unroll") for (int j = 0; j < NL; ++j)                      \
+        _Pragma("unroll") for (int i = 0; i < R; ++i) {                     \
+            const u32 v_ = lds32<((H) - 1) * 8>(a[j][i]);                   \
+            if (v_ < x[i]) a[j][i] += (H) * 8;                              \
+        }                                                                   \
     }
-    switch (l2) {
+    switch (l2P) {
         case 15: DGX_L32(16384)
         case 14: DGX_L32(8192)
         case 13: DGX_L32(4096)
@@ -334,10 +349,12 @@ __device__ __forceinline__ unsigned lift32(u32 sb, u32 n, const u32 (&x)[R]) {
         default: break;
     }
 #undef DGX_L32
-    unsigned hit = 0;
 #pragma unroll
-    for (int i = 0; i < R; ++i) hit |= (lds32r(a[i]) == x[i]) ? (1u << i) : 0u;
-    return hit;
+    for (int j = 0; j < NL; ++j) {
+        hit[j] = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) hit[j] |= (lds32r(a[j][i]) == x[i]) ? (1u << i) : 0u;
+    }
 }
 
 #ifdef DGX_PIPE_PROF
@@ -628,25 +645,68 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                 for (int i = 0; i < P_VA; ++i) x[i] = (u32)c[i];
                 const u32 slb = smem_u32(sl);
                 const bool keep_hits = P.op == 0;
-                for (; t < km1 && rows > 0; ++t) {
-                    const u32 n = G.n[t];
-                    unsigned hit = 0;
-                    if (n != 0) {
-                        const u32 sb = slb + G.off[t] * 8u;
-                        if (rows == 1) {
-                            const u32 x1[1] = {x[0]};
-                            hit = lift32<1>(sb, n, x1);
-                        } else if (P_VA == 2 || rows == 2) {
-                            const u32 x2[2] = {x[0], x[1]};
-                            hit = lift32<2>(sb, n, x2);
-                        } else {
-                            hit = lift32<P_VA>(sb, n, x);
+                while (t < km1 && rows > 0) {
+                    if (rows >= 2) {
+                        // ---- every row of the warp against ONE list (rows chains) ----------------------
+                        const u32 nn[1] = {G.n[t]};
+                        unsigned hit[1] = {0};
+                        if (nn[0] != 0) {
+                            const u32 sbs[1] = {slb + G.off[t] * 8u};
+                            const int l2 = 31 - __clz(nn[0]);
+                            if (P_VA == 2 || rows == 2) {
+                                const u32 x2[2] = {x[0], x[1]};
+                                lift32m<2, 1>(sbs, nn, l2, x2, hit);
+                            } else {
+                                lift32m<P_VA, 1>(sbs, nn, l2, x, hit);
+                            }
                         }
+                        alive &= keep_hits ? hit[0] : ~hit[0];
+                        t += 1;
+                    } else {
+                        // ---- one row against up to three lists at once (speculative: a candidate that fails the
+                        //      first is searched in the others anyway -- the lanes are there, the chains overlap) ----
+                        u32 g = km1 - t < 3u ? km1 - t : 3u;
+                        u32 nn[3], sbs[3];
+                        u32 nmin = 0xffffffffu, nmax = 0;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const u32 tj = (u32)j < g ? t + j : t;
+                            nn[j] = G.n[tj];
+                            sbs[j] = slb + G.off[tj] * 8u;
+                            nmin = nn[j] < nmin ? nn[j] : nmin;
+                            nmax = nn[j] > nmax ? nn[j] : nmax;
+                        }
+                        const u32 x1[1] = {x[0]};
+                        unsigned ok = 1u;
+                        if (nmin == 0) {
+                            // an empty slice: nothing survives an intersection; a difference (one list) keeps everything
+                            ok = keep_hits ? 0u : 1u;
+                            g = keep_hits ? g : 1u;
+                        } else {
+                            int l2 = 31 - __clz(nmin);
+                            if (nmax > 3u << l2) { g = 1; l2 = 31 - __clz(nn[0]); }  // lengths too far apart for one ladder
+                            unsigned h3[3] = {0, 0, 0};
+                            if (g == 3) {
+                                lift32m<1, 3>(sbs, nn, l2, x1, h3);
+                                ok = h3[0] & h3[1] & h3[2] & 1u;
+                            } else if (g == 2) {
+                                const u32 s2[2] = {sbs[0], sbs[1]}, n2[2] = {nn[0], nn[1]};
+                                unsigned h2[2] = {0, 0};
+                                lift32m<1, 2>(s2, n2, l2, x1, h2);
+                                ok = h2[0] & h2[1] & 1u;
+                            } else {
+                                const u32 s1[1] = {sbs[0]}, n1[1] = {nn[0]};
+                                unsigned h1[1] = {0};
+                                lift32m<1, 1>(s1, n1, l2, x1, h1);
+                                ok = keep_hits ? (h1[0] & 1u) : (~h1[0] & 1u);
+                            }
+                        }
+                        alive &= ok;
+                        t += g;
                     }
-                    alive &= keep_hits ? hit : ~hit;
-                    if (t + 1 < km1 && rows == 1) {
+                    if (t < km1 && rows == 1) {
                         if (!__any_sync(0xffffffffu, alive & 1u)) { rows = 0; alive = 0; }  // nobody left: done with the tile
-                    } else if (t + 1 < km1) {
+                    } else if (t < km1) {
                         // re-pack into fewer rows (order preserved)
                         unsigned b[P_VA];
                         int tot = 0;

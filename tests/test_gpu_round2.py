@@ -64,18 +64,18 @@ def test_intersect_sorted_packed(dgx, orc):
     for k, p, bs in ((1, 0.5, 256), (2, 0.5, 256), (3, 0.3, 10), (8, 0.25, 256), (8, 0.9, 256), (12, 0.8, 64)):
         lists = [gen.thin(rng, master, p) for _ in range(k)]
         packs = [to_pack(dgx, orc.encode(l, bs)) for l in lists]
-        got = dgx.algo.IntersectSortedPacked(packs)
+        got = dgx.algo.IntersectSortedPacks(packs)
         eq(got.Uids, orc.intersect_sorted(lists), f"packed k={k} p={p} bs={bs}")
     # nil / empty packs: the empty list; no packs: &pb.List{}
     lists = [gen.thin(rng, master, 0.5) for _ in range(3)]
     packs = [to_pack(dgx, orc.encode(l, 256)) for l in lists]
-    assert dgx.algo.IntersectSortedPacked(packs[:2] + [None]).tolist() == []
-    assert dgx.algo.IntersectSortedPacked([]).Uids is None
+    assert dgx.algo.IntersectSortedPacks(packs[:2] + [None]).tolist() == []
+    assert dgx.algo.IntersectSortedPacks([]).Uids is None
     # values across 32-bit-MSB block splits and at the top of the range
     hi = np.sort(rng.integers(2**63, 2**64 - 1, 50_000, dtype=np.uint64))
     hi = np.unique(hi)
     a, b = hi[rng.random(hi.size) < 0.7], hi[rng.random(hi.size) < 0.7]
-    got = dgx.algo.IntersectSortedPacked([to_pack(dgx, orc.encode(a, 256)), to_pack(dgx, orc.encode(b, 256))])
+    got = dgx.algo.IntersectSortedPacks([to_pack(dgx, orc.encode(a, 256)), to_pack(dgx, orc.encode(b, 256))])
     eq(got.Uids, orc.intersect_sorted([a, b]), "packed full-range")
 
 
@@ -95,9 +95,9 @@ def test_pack_cache(dgx, orc):
     h0, m0 = st.hits, st.misses
     keys = [(1000 + i, 7) for i in range(4)]
     h2d0 = _lib.stats()["h2d_bytes"]
-    eq(dgx.algo.IntersectSortedPacked(packs, keys).Uids, want, "cache cold")
+    eq(dgx.algo.IntersectSortedPacks(packs, keys).Uids, want, "cache cold")
     h2d1 = _lib.stats()["h2d_bytes"]
-    eq(dgx.algo.IntersectSortedPacked(packs, keys).Uids, want, "cache warm")
+    eq(dgx.algo.IntersectSortedPacks(packs, keys).Uids, want, "cache warm")
     h2d2 = _lib.stats()["h2d_bytes"]
     lib.dgx_cache_get_stats(C.byref(st))
     assert st.misses - m0 == 4 and st.hits - h0 == 4 and st.entries >= 4
@@ -106,17 +106,17 @@ def test_pack_cache(dgx, orc):
     # a new version of a key names different bytes: it must not hit the old entry
     lists2 = [gen.thin(rng, master, 0.4) for _ in range(4)]
     packs2 = [to_pack(dgx, orc.encode(l, 256)) for l in lists2]
-    eq(dgx.algo.IntersectSortedPacked(packs2, [(1000 + i, 8) for i in range(4)]).Uids, orc.intersect_sorted(lists2), "new version")
+    eq(dgx.algo.IntersectSortedPacks(packs2, [(1000 + i, 8) for i in range(4)]).Uids, orc.intersect_sorted(lists2), "new version")
     # eviction: a cache that holds about two packs still answers correctly and stays within its budget
     one = lib.dgx_cache_get_stats
     _lib.check(lib.dgx_cache_configure(int(2.5 * packs[0].deltas.size)))
     for rep in range(3):
-        eq(dgx.algo.IntersectSortedPacked(packs, [(2000 + i, 1) for i in range(4)]).Uids, want, f"evicting rep {rep}")
+        eq(dgx.algo.IntersectSortedPacks(packs, [(2000 + i, 1) for i in range(4)]).Uids, want, f"evicting rep {rep}")
     one(C.byref(st))
     assert st.bytes <= st.max_bytes and st.evictions > 0
     # disabled cache: named packs still work (one-shot copies)
     _lib.check(lib.dgx_cache_configure(0))
-    eq(dgx.algo.IntersectSortedPacked(packs, keys).Uids, want, "cache disabled")
+    eq(dgx.algo.IntersectSortedPacks(packs, keys).Uids, want, "cache disabled")
     one(C.byref(st))
     assert st.entries == 0
     _lib.check(lib.dgx_cache_configure(32 << 30))
@@ -136,7 +136,7 @@ def test_pack_cache_concurrent(dgx, orc):
             r = np.random.default_rng(t)
             for _ in range(8):
                 sel = sorted(r.choice(6, 3, replace=False).tolist())
-                got = dgx.algo.IntersectSortedPacked([packs[i] for i in sel], [(3000 + i, 1) for i in sel])
+                got = dgx.algo.IntersectSortedPacks([packs[i] for i in sel], [(3000 + i, 1) for i in sel])
                 eq(got.Uids, orc.intersect_sorted([lists[i] for i in sel]), f"thread {t} {sel}")
         except Exception as e:  # noqa: BLE001
             errs.append(e)
