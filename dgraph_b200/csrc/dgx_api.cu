@@ -76,6 +76,8 @@ static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's sli
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
+static int g_prepass_overlap = 1;      // DGX_PREPASS_OVERLAP=0: plan pre-pass serialised in front of the pipeline kernel
+static int g_zero_copy = 1;            // DGX_ZERO_COPY=0: always stage packs through cudaMemcpyAsync
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
 static int g_num_sms = 148;
@@ -173,6 +175,8 @@ struct dgx_lane {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;       // pre-pass of a filter batch, concurrent with its pipeline kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevArena ws;
     HostArena host;
     int* d_err = nullptr;   // device error flag (out_cap overflow)
@@ -232,6 +236,22 @@ extern "C" int dgx_init(int device) {
     numa_probe(device);
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
     if (const char* s = getenv("DGX_MERGE")) g_merge_multi = (strcmp(s, "tree") != 0);
+    if (const char* s = getenv("DGX_ZERO_COPY")) g_zero_copy = atoi(s) != 0;
+    if (const char* s = getenv("DGX_PREPASS_OVERLAP")) g_prepass_overlap = atoi(s) != 0;
+    {
+        // The overlap needs a pre-pass CTA (128 threads) to fit on an SM NEXT to two resident pipeline CTAs: the
+        // pipeline polls the pre-pass tables and would spin forever if the pre-pass could not be scheduled.
+        cudaFuncAttributes fa_pipe, fa_plan, fa_tiles;
+        CK(cudaFuncGetAttributes(&fa_pipe, filter_pipe_kernel));
+        CK(cudaFuncGetAttributes(&fa_plan, filter_plan_kernel));
+        CK(cudaFuncGetAttributes(&fa_tiles, filter_tiles_kernel));
+        auto regs_of = [](int per_thread, int threads) { return ((per_thread + 7) / 8 * 8) * ((threads + 31) / 32 * 32); };
+        const int pipe_regs = 2 * regs_of(fa_pipe.numRegs, P_NT);
+        const int pre_regs = std::max(regs_of(fa_plan.numRegs, 128), regs_of(fa_tiles.numRegs, 128));
+        const bool fits = pipe_regs + pre_regs <= prop.regsPerMultiprocessor && 2 * P_NT + 128 <= prop.maxThreadsPerMultiProcessor &&
+                          fa_plan.sharedSizeBytes == 0 && fa_tiles.sharedSizeBytes == 0;
+        if (!fits) g_prepass_overlap = 0;
+    }
     if (const char* s = getenv("DGX_MERGE_MULTI_MIN")) g_merge_multi_min = (size_t)atoll(s);
     if (const char* s = getenv("DGX_PIPE_MIN_K")) g_pipe_min_k = (size_t)std::max(1, atoi(s));
     if (const char* s = getenv("DGX_SCAP")) {
@@ -350,6 +370,13 @@ extern "C" dgx_lane* dgx_lane_create(int device, void* stream) {
         if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; return nullptr; }
         l->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        fail(DGX_ERR_CUDA, "lane side stream failed");
+        delete l;
+        return nullptr;
+    }
     if (cudaMalloc(&l->d_err, 256) != cudaSuccess ||
         pinned_alloc((void**)&l->h_err, 4096 + kSpecHead * sizeof(uint64_t)) != cudaSuccess) {
         fail(DGX_ERR_OOM, "lane allocation failed");
@@ -371,6 +398,9 @@ extern "C" void dgx_lane_destroy(dgx_lane* l) {
     l->host.destroy();
     if (l->d_err) cudaFree(l->d_err);
     if (l->h_err) cudaFreeHost(l->h_err);
+    if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
+    if (l->ev_fork) cudaEventDestroy(l->ev_fork);
+    if (l->ev_join) cudaEventDestroy(l->ev_join);
     if (l->own_stream) cudaStreamDestroy(l->stream);
     delete l;
 }
@@ -518,20 +548,33 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         rc = l->ws.alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
         if (rc) return rc;
         CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, l->stream));
-        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
-                                                                                      P.ntiles, (PTileEntry*)d_tiles);
+        // The pre-pass tables start as all-ones = "not written": filter_pipe_kernel polls them, so the pre-pass
+        // can run on the lane's side stream CONCURRENTLY with the pipeline kernel (it is ~7x faster than the
+        // pipeline consumes tiles; only the first few claims ever wait).  Both need the same inputs, so the side
+        // stream forks after everything queued so far and joins before anything queued later.
+        CK(cudaMemsetAsync(d_tiles, 0xFF, ntiles * sizeof(PTileEntry), l->stream));
+        CK(cudaMemsetAsync(d_plan, 0xFF, (npairs + 1) * sizeof(PPlanEntry), l->stream));
+        cudaStream_t pre = l->stream;
+        if (g_prepass_overlap) {
+            CK(cudaEventRecord(l->ev_fork, l->stream));
+            CK(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
+            pre = l->side;
+        }
+        filter_tiles_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
+                                                                            P.ntiles, (PTileEntry*)d_tiles);
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;
         if (npairs) {
-            const u64 blocks = (npairs + 255) / 256;
+            const u64 blocks = (npairs + 127) / 128;
             if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
-            filter_plan_kernel<<<(unsigned)blocks, 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
-                                                                         (PPlanEntry*)d_plan);
+            filter_plan_kernel<<<(unsigned)blocks, 128, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
+                                                                (PPlanEntry*)d_plan);
             CK(cudaGetLastError());
             l->launches += 1;
             g_stats.launches += 1;
         }
+        if (g_prepass_overlap) CK(cudaEventRecord(l->ev_join, l->side));
         PParams PP;
         PP.f = P;
         PP.plan_base = (const u64*)d_pb;
@@ -557,6 +600,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;
+        if (g_prepass_overlap) CK(cudaStreamWaitEvent(l->stream, l->ev_join, 0));
     }
     g_stats.uids_in += uids_in;
     return DGX_OK;
@@ -867,6 +911,7 @@ static void pack_point(dgx_dev_pack* out, const dgx_pack_view* v, const PackLayo
     out->pk.num = (const u32*)(d_meta + L.o_num);
     out->pk.deltas = (const unsigned char*)d_deltas;
     out->pk.max_num = max_num;
+    out->pk.sysmem = 0;
     out->bytes = L.meta_bytes + L.dpad;
     out->exact_len = exact_len;
     out->block_size = v ? v->block_size : 0;
@@ -900,6 +945,84 @@ static int pack_upload_impl(dgx_lane* l, const dgx_pack_view* v, void* d_mem_or_
     g_stats.h2d += L.meta_bytes + L.dbytes;
     pack_point(out, v, L, d, d + L.meta_bytes, exact, max_num);
     out->d_mem = d_mem;
+    return DGX_OK;
+}
+
+// Device-usable alias of a pinned (cudaMallocHost / cudaHostRegister'ed, mapped) host pointer, or nullptr.
+static const void* mapped_host_ptr(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+// Zero-copy form of packs_upload_ws: when every array of every pack is pinned host memory the decode kernel
+// reads base / NumUids / delta_off / deltas directly over PCIe; only uid_off (computed here while the block table
+// is validated) is copied, one small transfer for the whole call.  Returns DGX_OK with *done = false when some
+// array is pageable (the caller then stages through DMA copies).
+static int packs_map_ws(dgx_lane* l, const dgx_pack_view* const* views, size_t k, dgx_dev_pack* outs, bool* done) {
+    *done = false;
+    if (!g_zero_copy) return DGX_OK;
+    struct Dev { const void *base, *num, *doff, *del; };
+    std::vector<Dev> dv(k);
+    size_t uoff_total = 0;
+    for (size_t i = 0; i < k; ++i) {
+        const dgx_pack_view* v = views[i];
+        if (!v) continue;
+        if (v->nblocks == 0) return DGX_OK;  // empty views carry no arrays: take the generic path
+        dv[i] = {mapped_host_ptr(v->base), mapped_host_ptr(v->num_uids), mapped_host_ptr(v->delta_off), mapped_host_ptr(v->deltas)};
+        if (!dv[i].base || !dv[i].num || !dv[i].doff || !dv[i].del) return DGX_OK;
+        if ((reinterpret_cast<uintptr_t>(dv[i].del) & 15u) || (reinterpret_cast<uintptr_t>(dv[i].base) & 7u) ||
+            (reinterpret_cast<uintptr_t>(dv[i].doff) & 7u) || (reinterpret_cast<uintptr_t>(dv[i].num) & 3u))
+            return DGX_OK;
+        uoff_total += (v->nblocks + 1) * sizeof(uint64_t);
+    }
+    if (uoff_total == 0) return DGX_OK;
+    void *d_raw, *h_raw;
+    int rc = l->ws.alloc(uoff_total, &d_raw);
+    if (rc) return rc;
+    rc = l->host.alloc(uoff_total, &h_raw);
+    if (rc) return rc;
+    size_t o = 0;
+    for (size_t i = 0; i < k; ++i) {
+        const dgx_pack_view* v = views[i];
+        if (!v) continue;
+        const size_t nb = v->nblocks;
+        uint64_t* h_uoff = (uint64_t*)((char*)h_raw + o);
+        uint64_t acc = 0;
+        uint32_t max_num = 0;
+        for (size_t b = 0; b < nb; ++b) {
+            h_uoff[b] = acc;
+            const uint32_t num = v->num_uids[b];
+            acc += num;
+            max_num = std::max(max_num, num);
+            const uint64_t b0 = v->delta_off[b], b1 = v->delta_off[b + 1];
+            const uint64_t need = num > 1 ? 5ull * ((uint64_t)(num + 2) / 4) : 0;
+            if (b1 < b0 || b1 - b0 < need)
+                return fail(DGX_ERR_ARG, "malformed UidPack: block %zu has %lld delta bytes, NumUids %u needs >= %llu",
+                            b, (long long)(b1 - b0), num, (unsigned long long)need);
+        }
+        h_uoff[nb] = acc;
+        dgx_dev_pack& P = outs[i];
+        P.pk.nblocks = nb;
+        P.pk.base = (const u64*)dv[i].base;
+        P.pk.num = (const u32*)dv[i].num;
+        P.pk.delta_off = (const u64*)dv[i].doff;
+        P.pk.deltas = (const unsigned char*)dv[i].del;
+        P.pk.uid_off = (const u64*)((char*)d_raw + o);
+        P.pk.max_num = max_num;
+        P.pk.sysmem = 1;
+        P.d_mem = nullptr;
+        P.bytes = 0;
+        P.exact_len = acc;
+        P.block_size = v->block_size;
+        o += (nb + 1) * sizeof(uint64_t);
+        // the bytes still cross PCIe, as reads issued by the decode kernel
+        g_stats.h2d += nb * 20 + (nb + 1) * 8 + (size_t)v->delta_off[nb];
+    }
+    CK(cudaMemcpyAsync(d_raw, h_raw, uoff_total, cudaMemcpyHostToDevice, l->stream));
+    *done = true;
     return DGX_OK;
 }
 
@@ -1519,7 +1642,9 @@ extern "C" int dgx_intersect_sorted_packed(const dgx_pack_ref* refs, size_t k, u
     }
     if (rc == DGX_OK) {
         std::vector<dgx_dev_pack> up(k);
-        rc = packs_upload_ws(l, oneshot.data(), k, up.data());
+        bool mapped = false;
+        rc = packs_map_ws(l, oneshot.data(), k, up.data(), &mapped);  // pinned packs are decoded in place (zero-copy)
+        if (rc == DGX_OK && !mapped) rc = packs_upload_ws(l, oneshot.data(), k, up.data());
         for (size_t i = 0; i < k && rc == DGX_OK; ++i)
             if (oneshot[i]) pls[i].pk = up[i];
     }

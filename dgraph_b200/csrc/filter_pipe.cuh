@@ -77,11 +77,30 @@ constexpr u32 P_END = 0xffffffffu;
 static_assert(P_CW * P_WC == P_TA, "tile geometry");
 
 struct PPlanEntry { u64 r0, r1; };
+// The pre-pass tables are preset to all-ones; a reader that runs concurrently with the pre-pass treats all-ones
+// words as "not written yet" (positions are < 2^63, the tile flag is 0 when complete).
+constexpr u64 P_NOT_READY = ~0ull;
+constexpr u32 P_NOT_READY32 = ~0u;
+__device__ __forceinline__ u64 ld_cg64(const u64* p) {  // L2-coherent load (no L1 allocation): sees a concurrent kernel's stores
+    u64 v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ PPlanEntry plan_wait(const PPlanEntry* p) {
+    PPlanEntry e;
+    while (true) {
+        e.r0 = ld_relaxed(&p->r0);
+        e.r1 = ld_relaxed(&p->r1);
+        if (e.r0 != P_NOT_READY && e.r1 != P_NOT_READY) return e;
+        __nanosleep(200);
+    }
+}
 struct PTileEntry {            // everything the metadata warp needs about a tile, resolved by filter_tiles_kernel
     u32 task, list_first, k, na;
     u64 a0, plan_idx, prev;
-    u32 has_prev, pad;
+    u32 has_prev, pad;         // pad: ready flag (see filter_tiles_kernel)
 };
+static_assert(sizeof(PTileEntry) == 48, "PTileEntry layout is read word by word");
 
 struct PParams {
     FParams f;                 // tasks, lists, op, outputs, look-back state (ticket unused)
@@ -157,8 +176,12 @@ __global__ void __launch_bounds__(256) filter_tiles_kernel(const FTask* __restri
     e.plan_idx = plan_base[lo] + ((u64)tile - T.tile_base) * (u64)(T.k - 1);
     e.has_prev = (e.a0 > 0 && e.na > 0) ? 1u : 0u;
     e.prev = e.has_prev ? ld_probe(LA.ptr + e.a0 - 1) : 0;
-    e.pad = 0;
+    // `pad` doubles as the ready flag (the table is preset to 0xFF; 0 = entry complete): filter_pipe_kernel may
+    // run CONCURRENTLY with this pre-pass and polls it, so it is written last, after a fence
+    e.pad = P_NOT_READY32;
     tiles[tile] = e;
+    __threadfence();
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&tiles[tile].pad), "r"(0u) : "memory");
 }
 
 // ---- pipeline state in shared memory -------------------------------------------------
@@ -429,7 +452,21 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             const u32 tile = valid ? (u32)tile64 : P_END;
             PTileEntry e;
             e.task = 0; e.list_first = 0; e.k = 0; e.na = 0; e.a0 = 0; e.plan_idx = 0; e.prev = 0; e.has_prev = 0;
-            if (valid) e = PP.tiles[tile];
+            if (valid) {
+                const PTileEntry* te = PP.tiles + tile;
+                u32 flag;
+                while (true) {  // the pre-pass may still be running (side stream): wait for the entry's ready flag
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(&te->pad) : "memory");
+                    if (flag != P_NOT_READY32) break;
+                    __nanosleep(200);
+                }
+                __threadfence();
+                const u64* w = reinterpret_cast<const u64*>(te);  // {task,list_first} {k,na} a0 plan_idx prev {has_prev,pad}
+                const u64 w0 = ld_cg64(w), w1 = ld_cg64(w + 1), w5 = ld_cg64(w + 5);
+                e.task = (u32)w0; e.list_first = (u32)(w0 >> 32); e.k = (u32)w1; e.na = (u32)(w1 >> 32);
+                e.a0 = ld_cg64(w + 2); e.plan_idx = ld_cg64(w + 3); e.prev = ld_cg64(w + 4);
+                e.has_prev = (u32)w5; e.pad = 0;
+            }
             u64 r0 = 0, r1 = 0, lenj = 0;
             const u64* ptrj = nullptr;
             const u64* A = nullptr;
@@ -438,7 +475,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                     const FList Lj = P.lists[e.list_first + 1 + u];
                     ptrj = Lj.ptr;
                     lenj = flist_len(Lj);
-                    const PPlanEntry pe = PP.plan[e.plan_idx + u];
+                    const PPlanEntry pe = plan_wait(PP.plan + e.plan_idx + u);
                     r0 = pe.r0; r1 = pe.r1;
                 }
                 if (u == 0) A = P.lists[e.list_first].ptr;
@@ -804,7 +841,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                     const FList Lj = P.lists[G.list_first + 1 + t];
                     const u64* __restrict__ B = Lj.ptr;
                     const u64 lenB = flist_len(Lj);
-                    const PPlanEntry e = PP.plan[G.plan_idx + t];
+                    const PPlanEntry e = plan_wait(PP.plan + G.plan_idx + t);
                     const u64 sz = e.r1 - e.r0;
 #pragma unroll
                     for (int i = 0; i < P_VA; ++i) {

@@ -1,10 +1,11 @@
 #!/bin/bash
-# A/B of library builds on the headline step (device-resident, no e2e/ops): tools/ab.sh libdgx.so libdgx_X.so ...
-for lib in "$@"; do
-  out=$(DGX_LIB=$PWD/dgraph_b200/$lib timeout 200 python bench.py --steps 50 --warmup 5 --no-e2e --no-ops 2>gpurun_out/ab_$lib.err | tail -1)
+# A/B of library builds on the headline step (device-resident, no e2e/ops): tools/ab.sh libdgx.so libdgx_X.so:ENV=VAL ...
+for spec in "$@"; do
+  lib=${spec%%:*}; envs=""; [[ "$spec" == *:* ]] && envs=${spec#*:}
+  out=$(env ${envs//,/ } DGX_LIB=$PWD/dgraph_b200/$lib timeout 200 python bench.py --steps 50 --warmup 5 --no-e2e --no-ops 2>gpurun_out/ab_err.log | tail -1)
   echo "$out" | python -c '
 import sys,json
 d=json.loads(sys.stdin.read())
 dv=d.get("dense_variant") or {}
-print("'$lib' :: C2 %.4f ms frac %.3f exact %s :: dense %.4f ms frac %.3f exact %s" % (d["ms_per_step"], d["roofline"]["frac"], d["bit_exact"], dv.get("ms_per_step",0), dv.get("roofline_frac",0), dv.get("bit_exact")))'
+print("'$spec' :: C2 %.4f ms frac %.3f exact %s :: dense %.4f ms frac %.3f exact %s" % (d["ms_per_step"], d["roofline"]["frac"], d["bit_exact"], dv.get("ms_per_step",0), dv.get("roofline_frac",0), dv.get("bit_exact")))' || tail -3 gpurun_out/ab_err.log
 done
