@@ -76,6 +76,8 @@ SYMBOLS = {
     "dgx_difference_packed": (_int, [C.POINTER(PackRef), C.POINTER(PackRef), C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
     "dgx_intersect_sorted_packed_out": (_int, [C.POINTER(PackRef), _sz, C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
     "dgx_merge_sorted_packed": (_int, [C.POINTER(PackRef), _sz, C.c_uint32, _vp, _vp, _vp, _vp, _szp, _szp, C.POINTER(PackView)]),
+    "dgx_pack_image_size": (_sz, [_sz, _sz]),
+    "dgx_pack_image_view": (_int, [_vp, C.c_uint32, _sz, _sz, C.POINTER(PackView)]),
     "dgx_cache_configure": (_int, [_sz]),
     "dgx_cache_clear": (None, []),
     "dgx_cache_get_stats": (None, [C.POINTER(CacheStats)]),

@@ -77,7 +77,7 @@ constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
 static int g_prepass_overlap = 1;      // DGX_PREPASS_OVERLAP=0: plan pre-pass serialised in front of the pipeline kernel
-static int g_zero_copy = 1;            // DGX_ZERO_COPY=0: always stage packs through cudaMemcpyAsync
+static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
 static int g_num_sms = 148;
@@ -1028,7 +1028,93 @@ static int packs_map_ws(dgx_lane* l, const dgx_pack_view* const* views, size_t k
 
 // The k packs of one call into the lane's workspace: one copy for all metadata images, one per pack
 // for its delta bytes (straight from the caller's memory).  views[i] == nullptr entries are skipped.
+// Flat image of a pack (dgx_pack_image_size / dgx_pack_image_view): [base u64 x nb | delta_off u64 x (nb+1) |
+// num_uids u32 x nb | pad to 16 | deltas | pad to 16].  A shim that flattens pb.UidPack.Blocks into pinned staging
+// memory writes this directly; images written back to back travel as ONE DMA transfer.
+static size_t image_meta_bytes(size_t nb) { return (nb * 8 + (nb + 1) * 8 + nb * 4 + 15) & ~size_t(15); }
+static bool view_is_image(const dgx_pack_view* v) {
+    const size_t nb = v->nblocks;
+    const char* b = (const char*)v->base;
+    if (!b || (reinterpret_cast<uintptr_t>(b) & 15u)) return false;
+    return (const char*)v->delta_off == b + nb * 8 && (const char*)v->num_uids == b + nb * 8 + (nb + 1) * 8 &&
+           (const char*)v->deltas == b + image_meta_bytes(nb);
+}
+static size_t view_image_bytes(const dgx_pack_view* v) {
+    return image_meta_bytes(v->nblocks) + (((size_t)v->delta_off[v->nblocks] + 15) & ~size_t(15));
+}
+// All packs of the call are images laid out back to back: one copy for the images, one for the uid_off tables.
+static int packs_upload_run(dgx_lane* l, const dgx_pack_view* const* views, size_t k, dgx_dev_pack* outs, bool* done) {
+    *done = false;
+    const char* start = nullptr;
+    const char* next = nullptr;
+    size_t uoff_bytes = 0;
+    for (size_t i = 0; i < k; ++i) {
+        const dgx_pack_view* v = views[i];
+        if (!v) continue;
+        if (v->nblocks == 0 || !view_is_image(v)) return DGX_OK;
+        if (!start) start = (const char*)v->base;
+        else if ((const char*)v->base != next) return DGX_OK;
+        next = (const char*)v->base + view_image_bytes(v);
+        uoff_bytes += (v->nblocks + 1) * sizeof(uint64_t);
+    }
+    if (!start) return DGX_OK;
+    const size_t run = (size_t)(next - start);
+    void *d_img, *d_uoff, *h_uoff;
+    int rc = l->ws.alloc(run + 64, &d_img);
+    if (rc) return rc;
+    rc = l->ws.alloc(uoff_bytes, &d_uoff);
+    if (rc) return rc;
+    rc = l->host.alloc(uoff_bytes, &h_uoff);
+    if (rc) return rc;
+    size_t uo = 0;
+    for (size_t i = 0; i < k; ++i) {
+        const dgx_pack_view* v = views[i];
+        if (!v) continue;
+        const size_t nb = v->nblocks;
+        uint64_t* hu = (uint64_t*)((char*)h_uoff + uo);
+        uint64_t acc = 0;
+        uint32_t max_num = 0;
+        for (size_t b = 0; b < nb; ++b) {
+            hu[b] = acc;
+            const uint32_t num = v->num_uids[b];
+            acc += num;
+            max_num = std::max(max_num, num);
+            const uint64_t b0 = v->delta_off[b], b1 = v->delta_off[b + 1];
+            const uint64_t need = num > 1 ? 5ull * ((uint64_t)(num + 2) / 4) : 0;
+            if (b1 < b0 || b1 - b0 < need)
+                return fail(DGX_ERR_ARG, "malformed UidPack: block %zu has %lld delta bytes, NumUids %u needs >= %llu",
+                            b, (long long)(b1 - b0), num, (unsigned long long)need);
+        }
+        hu[nb] = acc;
+        char* d = (char*)d_img + ((const char*)v->base - start);
+        dgx_dev_pack& P = outs[i];
+        P.pk.nblocks = nb;
+        P.pk.base = (const u64*)d;
+        P.pk.delta_off = (const u64*)(d + nb * 8);
+        P.pk.num = (const u32*)(d + nb * 8 + (nb + 1) * 8);
+        P.pk.deltas = (const unsigned char*)(d + image_meta_bytes(nb));
+        P.pk.uid_off = (const u64*)((char*)d_uoff + uo);
+        P.pk.max_num = max_num;
+        P.pk.sysmem = 0;
+        P.d_mem = nullptr;
+        P.bytes = view_image_bytes(v);
+        P.exact_len = acc;
+        P.block_size = v->block_size;
+        uo += (nb + 1) * sizeof(uint64_t);
+    }
+    CK(cudaMemcpyAsync(d_img, start, run, cudaMemcpyHostToDevice, l->stream));
+    CK(cudaMemcpyAsync(d_uoff, h_uoff, uoff_bytes, cudaMemcpyHostToDevice, l->stream));
+    g_stats.h2d += run + uoff_bytes;
+    *done = true;
+    return DGX_OK;
+}
+
 static int packs_upload_ws(dgx_lane* l, const dgx_pack_view* const* views, size_t k, dgx_dev_pack* outs) {
+    {
+        bool done = false;
+        int rc0 = packs_upload_run(l, views, k, outs, &done);
+        if (rc0 || done) return rc0;
+    }
     std::vector<PackLayout> Ls(k);
     size_t meta_total = 0, del_total = 0;
     for (size_t i = 0; i < k; ++i) {
@@ -1749,6 +1835,22 @@ extern "C" int dgx_pack_seek(const dgx_pack_view* p, int kind, uint64_t uid, int
 // ---------------------------------------------------------------------------
 // codec.Encode on the device, packed set operations
 // ---------------------------------------------------------------------------
+extern "C" size_t dgx_pack_image_size(size_t nblocks, size_t delta_bytes) {
+    return image_meta_bytes(nblocks) + ((delta_bytes + 15) & ~size_t(15));
+}
+extern "C" int dgx_pack_image_view(void* image, uint32_t block_size, size_t nblocks, size_t delta_bytes, dgx_pack_view* view) {
+    (void)delta_bytes;
+    if (!image || !view || (reinterpret_cast<uintptr_t>(image) & 15u)) return fail(DGX_ERR_ARG, "image must be 16-byte aligned");
+    char* b = (char*)image;
+    view->block_size = block_size;
+    view->nblocks = nblocks;
+    view->base = (const uint64_t*)b;
+    view->delta_off = (const uint64_t*)(b + nblocks * 8);
+    view->num_uids = (const uint32_t*)(b + nblocks * 8 + (nblocks + 1) * 8);
+    view->deltas = (const uint8_t*)(b + image_meta_bytes(nblocks));
+    return DGX_OK;
+}
+
 extern "C" void dgx_encode_bound(size_t n, uint32_t block_size, size_t* nblocks_cap, size_t* delta_cap) {
     const size_t B = block_size ? block_size : 1;
     // a sorted list crosses a multiple of 2^32 rarely: room for 64 extra (short) blocks; dgx_encode reports the

@@ -83,6 +83,51 @@ def gatherv_contiguous(dist, local_out, local_off, device=None):
     return out_g, off_g
 
 
+def gatherv_exact(dist, parts, local_out, local_off, device=None):
+    """All-gatherv for CONTIGUOUS shards (contiguous_partition) with exact sizes: returns (out, off) in unit order,
+    identical on every rank.
+
+    1. one all_gather of the per-unit result lengths (shards padded to the largest shard's unit count, which is
+       static: the partition is computed from the inputs' sizes on every rank);
+    2. ONE host read of those lengths (the only synchronisation): offsets and per-rank totals follow on the host;
+    3. every rank's payload travels straight to its final position in `out` -- grouped point-to-point sends and
+       receives of the exact sizes (ncclGroupStart/End under NCCL), no padding to the largest shard, no scatter.
+    """
+    import torch
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    dev = local_out.device if device is None else device
+    n_r = [len(p) for p in parts]
+    max_u = max(max(n_r), 1)
+    lens_local = torch.zeros(max_u, dtype=torch.int64, device=dev)
+    if n_r[rank]:
+        lens_local[: n_r[rank]] = local_off[1: n_r[rank] + 1] - local_off[: n_r[rank]]
+    lens_all = torch.empty(world * max_u, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens_all, lens_local)
+    lens_host = lens_all.cpu().numpy().reshape(world, max_u)          # the one host synchronisation
+    tot = [int(lens_host[r, : n_r[r]].sum()) for r in range(world)]
+    lens_g = np.concatenate([lens_host[r, : n_r[r]] for r in range(world)]) if sum(n_r) else np.zeros(0, np.int64)
+    off_host = np.zeros(lens_g.size + 1, dtype=np.int64)
+    np.cumsum(lens_g, out=off_host[1:])
+    base = np.concatenate([[0], np.cumsum(tot)]).astype(np.int64)
+    out_g = torch.empty(max(int(base[-1]), 1), dtype=torch.int64, device=dev)
+    ops = []
+    for r in range(world):
+        if r == rank:
+            if tot[r]:
+                out_g[int(base[r]): int(base[r]) + tot[r]].copy_(local_out[: tot[r]])
+            continue
+        if tot[rank]:
+            ops.append(dist.P2POp(dist.isend, local_out[: tot[rank]], r))
+        if tot[r]:
+            ops.append(dist.P2POp(dist.irecv, out_g[int(base[r]): int(base[r]) + tot[r]], r))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out_g[: int(base[-1])], torch.from_numpy(off_host).to(dev)
+
+
 def shard_offsets(counts: np.ndarray) -> np.ndarray:
     out = np.zeros(counts.size + 1, dtype=np.int64)
     np.cumsum(counts, out=out[1:])
@@ -150,16 +195,24 @@ def gatherv_results(dist, local_units: np.ndarray, local_out, local_off, n_units
     return out_g[: int(off_g[-1].item())], off_g
 
 
-def run_sharded_pairs(dist, a_lists, b_lists, compute: Callable, device=None):
+def run_sharded_pairs(dist, a_lists, b_lists, compute: Callable, device=None, partition: str = "contiguous"):
     """Intersect pair i = (a_lists[i], b_lists[i]) for all i, sharded over the process group.
 
     compute(units, a_lists, b_lists) -> (out int64 tensor, off int64 tensor) for the units a
     rank owns (on a GPU box: one dgx_dev_filter_batch launch).  Returns results in pair order.
+    partition "contiguous" (default): shards are runs of consecutive pairs balanced by bytes, results come back
+    through gatherv_exact (one host sync, exact sizes).  "lpt": longest-processing-time partition (tighter balance
+    when a few pairs dominate) with the general, index-scattering gatherv_results.
     """
     world = dist.get_world_size()
     rank = dist.get_rank()
     costs = [8 * (len(a) + len(b)) for a, b in zip(a_lists, b_lists)]
-    parts = lpt_partition(costs, world)
+    if partition == "lpt":
+        parts = lpt_partition(costs, world)
+        mine = parts[rank]
+        out, off = compute(mine, a_lists, b_lists)
+        return gatherv_results(dist, mine, out, off, len(a_lists), device=device)
+    parts = contiguous_partition(costs, world)
     mine = parts[rank]
     out, off = compute(mine, a_lists, b_lists)
-    return gatherv_results(dist, mine, out, off, len(a_lists), device=device)
+    return gatherv_exact(dist, parts, out, off, device=device)

@@ -152,6 +152,14 @@ typedef struct dgx_pack_ref {
     uint64_t version;
 } dgx_pack_ref;
 
+/* Flat image of a pack: [base u64 x n | delta_off u64 x (n+1) | num_uids u32 x n | pad to 16 | deltas | pad to 16],
+ * 16-byte aligned.  A shim that flattens pb.UidPack.Blocks ([]*UidBlock, each with its own Deltas slice) into
+ * pinned staging memory can write this layout directly: dgx_pack_image_view points a dgx_pack_view at the arrays of
+ * an image buffer (the caller fills them), and the views of images placed back to back in one buffer cross PCIe
+ * as ONE transfer when passed to the same call (a DMA of every small array costs microseconds of set-up each). */
+size_t dgx_pack_image_size(size_t nblocks, size_t delta_bytes);
+int dgx_pack_image_view(void* image, uint32_t block_size, size_t nblocks, size_t delta_bytes, dgx_pack_view* view);
+
 /* algo.IntersectSorted over lists held as packs: codec.Decode(pack_i, 0) for every i
  * (codec/codec.go:444-452) then algo.IntersectSorted (algo/uidlist.go:297-329), the decoded lists
  * never leaving the device.  A NULL / empty pack is the empty list.  out_cap >= min_i ExactLen. */

@@ -65,12 +65,14 @@ def _worker(rank, world, port, ret):
             cat = np.concatenate(outs + [np.zeros(0, np.uint64)]).view(np.int64)
             return torch.from_numpy(cat.copy()), torch.from_numpy(off)
 
-        out, off = run_sharded_pairs(dist, A, B, compute)
-        out = out.numpy().view(np.uint64)
-        off = off.numpy()
-        ok = off.size == npairs + 1
-        for i in range(npairs):
-            ok = ok and np.array_equal(out[off[i]: off[i + 1]], orc.intersect_with(A[i], B[i]))
+        ok = True
+        for partition in ("contiguous", "lpt"):
+            out, off = run_sharded_pairs(dist, A, B, compute, partition=partition)
+            out = out.numpy().view(np.uint64)
+            off = off.numpy()
+            ok = ok and off.size == npairs + 1
+            for i in range(npairs):
+                ok = ok and np.array_equal(out[off[i]: off[i + 1]], orc.intersect_with(A[i], B[i]))
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

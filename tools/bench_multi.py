@@ -54,7 +54,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.pop("NCCL_DEBUG", None)
+    if os.environ.get("NCCL_DEBUG"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's log never goes to stdout (JSON lines only)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -112,7 +113,7 @@ def main():
     def c4_step():
         c4_compute()
         if world > 1:
-            res["g"] = shard.gatherv_contiguous(dist, out, off, device=dev)
+            res["g"] = shard.gatherv_exact(dist, parts, out, off, device=dev)
         else:
             res["g"] = (out, off)
 
@@ -183,7 +184,7 @@ def main():
         _lib.check(lib.dgx_dev_filter_batch(lane, _lib.OP_DIFFERENCE, p2, l2, k2, 1, C.c_void_p(dout.data_ptr()),
                                             tot_local, C.c_void_p(doff.data_ptr())))
         if world > 1 and gather:
-            res5["g"] = shard.gatherv_contiguous(dist, dout, doff, device=dev)
+            res5["g"] = shard.gatherv_exact(dist, [[0]] * world, dout, doff, device=dev)
         else:
             res5["g"] = (dout, doff)
 
