@@ -76,7 +76,6 @@ static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's sli
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
-static int g_prepass_overlap = 1;      // DGX_PREPASS_OVERLAP=0: plan pre-pass serialised in front of the pipeline kernel
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
@@ -175,8 +174,6 @@ struct dgx_lane {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t side = nullptr;       // pre-pass of a filter batch, concurrent with its pipeline kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevArena ws;
     HostArena host;
     int* d_err = nullptr;   // device error flag (out_cap overflow)
@@ -237,31 +234,6 @@ extern "C" int dgx_init(int device) {
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
     if (const char* s = getenv("DGX_MERGE")) g_merge_multi = (strcmp(s, "tree") != 0);
     if (const char* s = getenv("DGX_ZERO_COPY")) g_zero_copy = atoi(s) != 0;
-    if (const char* s = getenv("DGX_PREPASS_OVERLAP")) g_prepass_overlap = atoi(s) != 0;
-    {
-        // The overlap needs a pre-pass CTA (128 threads) to fit on an SM NEXT to two resident pipeline CTAs: the
-        // pipeline polls the pre-pass tables and would spin forever if the pre-pass could not be scheduled.
-        cudaFuncAttributes fa_pipe, fa_plan, fa_tiles;
-        CK(cudaFuncGetAttributes(&fa_pipe, filter_pipe_kernel));
-        CK(cudaFuncGetAttributes(&fa_plan, filter_plan_kernel));
-        CK(cudaFuncGetAttributes(&fa_tiles, filter_tiles_kernel));
-        auto regs_of = [](int per_thread, int threads) { return ((per_thread + 7) / 8 * 8) * ((threads + 31) / 32 * 32); };
-        const int pipe_regs = 2 * regs_of(fa_pipe.numRegs, P_NT);
-        const int pre_regs = std::max(regs_of(fa_plan.numRegs, 128), regs_of(fa_tiles.numRegs, 128));
-        const bool fits = pipe_regs + pre_regs <= prop.regsPerMultiprocessor && 2 * P_NT + 128 <= prop.maxThreadsPerMultiProcessor &&
-                          fa_plan.sharedSizeBytes == 0 && fa_tiles.sharedSizeBytes == 0;
-        if (!fits) g_prepass_overlap = 0;
-    }
-    if (const char* s = getenv("DGX_MERGE_MULTI_MIN")) g_merge_multi_min = (size_t)atoll(s);
-    if (const char* s = getenv("DGX_PIPE_MIN_K")) g_pipe_min_k = (size_t)std::max(1, atoi(s));
-    if (const char* s = getenv("DGX_SCAP")) {
-        int v = atoi(s);
-        if (v >= 1024 && v <= (int)kScapMax) g_scap_override = (u32)v & ~15u;
-    }
-    if (const char* s = getenv("DGX_STREAM_RATIO")) {
-        int v = atoi(s);
-        if (v >= 0) g_stream_ratio = (u32)v;
-    }
     g_device = device;
     return DGX_OK;
 }
@@ -370,13 +342,6 @@ extern "C" dgx_lane* dgx_lane_create(int device, void* stream) {
         if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; return nullptr; }
         l->own_stream = true;
     }
-    if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        fail(DGX_ERR_CUDA, "lane side stream failed");
-        delete l;
-        return nullptr;
-    }
     if (cudaMalloc(&l->d_err, 256) != cudaSuccess ||
         pinned_alloc((void**)&l->h_err, 4096 + kSpecHead * sizeof(uint64_t)) != cudaSuccess) {
         fail(DGX_ERR_OOM, "lane allocation failed");
@@ -398,9 +363,6 @@ extern "C" void dgx_lane_destroy(dgx_lane* l) {
     l->host.destroy();
     if (l->d_err) cudaFree(l->d_err);
     if (l->h_err) cudaFreeHost(l->h_err);
-    if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
-    if (l->ev_fork) cudaEventDestroy(l->ev_fork);
-    if (l->ev_join) cudaEventDestroy(l->ev_join);
     if (l->own_stream) cudaStreamDestroy(l->stream);
     delete l;
 }
@@ -548,33 +510,20 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         rc = l->ws.alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
         if (rc) return rc;
         CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, l->stream));
-        // The pre-pass tables start as all-ones = "not written": filter_pipe_kernel polls them, so the pre-pass
-        // can run on the lane's side stream CONCURRENTLY with the pipeline kernel (it is ~7x faster than the
-        // pipeline consumes tiles; only the first few claims ever wait).  Both need the same inputs, so the side
-        // stream forks after everything queued so far and joins before anything queued later.
-        CK(cudaMemsetAsync(d_tiles, 0xFF, ntiles * sizeof(PTileEntry), l->stream));
-        CK(cudaMemsetAsync(d_plan, 0xFF, (npairs + 1) * sizeof(PPlanEntry), l->stream));
-        cudaStream_t pre = l->stream;
-        if (g_prepass_overlap) {
-            CK(cudaEventRecord(l->ev_fork, l->stream));
-            CK(cudaStreamWaitEvent(l->side, l->ev_fork, 0));
-            pre = l->side;
-        }
-        filter_tiles_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
-                                                                            P.ntiles, (PTileEntry*)d_tiles);
+        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
+                                                                                      P.ntiles, (PTileEntry*)d_tiles);
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;
         if (npairs) {
-            const u64 blocks = (npairs + 127) / 128;
+            const u64 blocks = (npairs + 255) / 256;
             if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
-            filter_plan_kernel<<<(unsigned)blocks, 128, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
-                                                                (PPlanEntry*)d_plan);
+            filter_plan_kernel<<<(unsigned)blocks, 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
+                                                                         (PPlanEntry*)d_plan);
             CK(cudaGetLastError());
             l->launches += 1;
             g_stats.launches += 1;
         }
-        if (g_prepass_overlap) CK(cudaEventRecord(l->ev_join, l->side));
         PParams PP;
         PP.f = P;
         PP.plan_base = (const u64*)d_pb;
@@ -600,7 +549,6 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;
-        if (g_prepass_overlap) CK(cudaStreamWaitEvent(l->stream, l->ev_join, 0));
     }
     g_stats.uids_in += uids_in;
     return DGX_OK;

@@ -77,35 +77,11 @@ constexpr u32 P_END = 0xffffffffu;
 static_assert(P_CW * P_WC == P_TA, "tile geometry");
 
 struct PPlanEntry { u64 r0, r1; };
-// The pre-pass tables are preset to all-ones; a reader that runs concurrently with the pre-pass treats all-ones
-// words as "not written yet" (positions are < 2^63, the tile flag is 0 when complete).
-constexpr u64 P_NOT_READY = ~0ull;
-constexpr u32 P_NOT_READY32 = ~0u;
-__device__ __forceinline__ u64 ld_cg64(const u64* p) {  // L2-coherent load (no L1 allocation): sees a concurrent kernel's stores
-    u64 v;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// Bounded wait for a plan entry of the (possibly still running) pre-pass: true when it arrived.  The pipeline
-// kernel NEVER depends on another kernel's progress: after P_POLLS misses the caller computes the entry itself
-// (plan_compute / tile_compute), so the pre-pass is an accelerator, not a dependency -- two persistent pipeline
-// kernels of different lanes cannot deadlock each other's pre-pass behind a shared hardware queue.
-constexpr int P_POLLS = 16;
-__device__ __forceinline__ bool plan_poll(const PPlanEntry* p, PPlanEntry& e) {
-    for (int i = 0; i < P_POLLS; ++i) {
-        e.r0 = ld_relaxed(&p->r0);
-        e.r1 = ld_relaxed(&p->r1);
-        if (e.r0 != P_NOT_READY && e.r1 != P_NOT_READY) return true;
-        __nanosleep(250);
-    }
-    return false;
-}
 struct PTileEntry {            // everything the metadata warp needs about a tile, resolved by filter_tiles_kernel
     u32 task, list_first, k, na;
     u64 a0, plan_idx, prev;
-    u32 has_prev, pad;         // pad: ready flag (see filter_tiles_kernel)
+    u32 has_prev, pad;
 };
-static_assert(sizeof(PTileEntry) == 48, "PTileEntry layout is read word by word");
 
 struct PParams {
     FParams f;                 // tasks, lists, op, outputs, look-back state (ticket unused)
@@ -118,30 +94,10 @@ struct PParams {
 };
 
 // ---- plan ---------------------------------------------------------------------------
-// Slice of list B (length lenB) that can hold a value of the tile A[a0 .. a0+na): r0 = first i with B[i] >= tile
-// first, r1 = first i with B[i] > tile last, as two interleaved binary searches.  A binary search touches one new
-// 32-byte sector per level only near its end (~8 sectors), where the 32-ary warp search of filter_kernel.cuh
-// touches ~70: the plan must not cost a second pass over HBM.
-__device__ __forceinline__ PPlanEntry plan_compute(const u64* __restrict__ A, u64 lenA, u64 a0, const u64* __restrict__ B, u64 lenB) {
-    PPlanEntry e;
-    e.r0 = 0; e.r1 = 0;
-    if (a0 < lenA) {
-        const u64 na = lenA - a0 < (u64)P_TA ? lenA - a0 : (u64)P_TA;
-        const u64 tlo = ld_probe(A + a0), thi = ld_probe(A + a0 + na - 1);
-        u64 l0 = 0, h0 = lenB, l1 = 0, h1 = h0;
-        while (l0 < h0 || l1 < h1) {
-            const u64 m0 = l0 + ((h0 - l0) >> 1), m1 = l1 + ((h1 - l1) >> 1);
-            const bool a = l0 < h0, c = l1 < h1;
-            const u64 v0 = a ? ld_probe(B + m0) : 0, v1 = c ? ld_probe(B + m1) : 0;
-            if (a) { if (v0 < tlo) l0 = m0 + 1; else h0 = m0; }
-            if (c) { if (v1 <= thi) l1 = m1 + 1; else h1 = m1; }
-        }
-        e.r0 = l0; e.r1 = l1;
-    }
-    return e;
-}
-
-// One THREAD per (tile, filter list).
+// One THREAD per (tile, filter list): r0 = first i with L[i] >= tile first, r1 = first i
+// with L[i] > tile last, as two interleaved binary searches.  A binary search touches one
+// new 32-byte sector per level only near its end (~8 sectors), where the 32-ary warp
+// search of filter_kernel.cuh touches ~70: the plan must not cost a second pass over HBM.
 __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
                                                           const u64* __restrict__ plan_base, u32 ntasks, u64 npairs,
                                                           PPlanEntry* __restrict__ plan) {
@@ -158,15 +114,34 @@ __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restric
     const u64 tl = local / km1;
     const u32 j = (u32)(local - tl * km1) + 1;
     const FList LA = lists[T.list_first];
-    const FList Lj = lists[T.list_first + j];
-    const PPlanEntry e = plan_compute(LA.ptr, flist_len(LA), tl * P_TA, Lj.ptr, flist_len(Lj));
-    plan[p].r0 = e.r0;
-    plan[p].r1 = e.r1;
+    const u64 lenA = flist_len(LA);
+    const u64 a0 = tl * P_TA;
+    u64 r0 = 0, r1 = 0;
+    if (a0 < lenA) {
+        const u64 na = lenA - a0 < (u64)P_TA ? lenA - a0 : (u64)P_TA;
+        const u64 tlo = ld_probe(LA.ptr + a0), thi = ld_probe(LA.ptr + a0 + na - 1);
+        const FList Lj = lists[T.list_first + j];
+        const u64* __restrict__ B = Lj.ptr;
+        u64 l0 = 0, h0 = flist_len(Lj), l1 = 0, h1 = h0;
+        while (l0 < h0 || l1 < h1) {
+            const u64 m0 = l0 + ((h0 - l0) >> 1), m1 = l1 + ((h1 - l1) >> 1);
+            const bool a = l0 < h0, c = l1 < h1;
+            const u64 v0 = a ? ld_probe(B + m0) : 0, v1 = c ? ld_probe(B + m1) : 0;
+            if (a) { if (v0 < tlo) l0 = m0 + 1; else h0 = m0; }
+            if (c) { if (v1 <= thi) l1 = m1 + 1; else h1 = m1; }
+        }
+        r0 = l0; r1 = l1;
+    }
+    plan[p].r0 = r0;
+    plan[p].r1 = r1;
 }
 
-// Which task a tile belongs to and where its driving values start.
-__device__ __forceinline__ PTileEntry tile_compute(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
-                                                   const u64* __restrict__ plan_base, u32 ntasks, u32 tile) {
+// One thread per tile: which task it belongs to and where its driving values start.
+__global__ void __launch_bounds__(256) filter_tiles_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
+                                                           const u64* __restrict__ plan_base, u32 ntasks, u32 ntiles,
+                                                           PTileEntry* __restrict__ tiles) {
+    const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
     u32 lo = 0, hi = ntasks;
     while (hi - lo > 1) {
         const u32 mid = (lo + hi) >> 1;
@@ -183,22 +158,7 @@ __device__ __forceinline__ PTileEntry tile_compute(const FTask* __restrict__ tas
     e.has_prev = (e.a0 > 0 && e.na > 0) ? 1u : 0u;
     e.prev = e.has_prev ? ld_probe(LA.ptr + e.a0 - 1) : 0;
     e.pad = 0;
-    return e;
-}
-
-// One thread per tile.
-__global__ void __launch_bounds__(256) filter_tiles_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
-                                                           const u64* __restrict__ plan_base, u32 ntasks, u32 ntiles,
-                                                           PTileEntry* __restrict__ tiles) {
-    const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= ntiles) return;
-    PTileEntry e = tile_compute(tasks, lists, plan_base, ntasks, tile);
-    // `pad` doubles as the ready flag (the table is preset to 0xFF; 0 = entry complete): filter_pipe_kernel may
-    // run CONCURRENTLY with this pre-pass and polls it, so it is written last, after a fence
-    e.pad = P_NOT_READY32;
     tiles[tile] = e;
-    __threadfence();
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&tiles[tile].pad), "r"(0u) : "memory");
 }
 
 // ---- pipeline state in shared memory -------------------------------------------------
@@ -469,25 +429,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
             const u32 tile = valid ? (u32)tile64 : P_END;
             PTileEntry e;
             e.task = 0; e.list_first = 0; e.k = 0; e.na = 0; e.a0 = 0; e.plan_idx = 0; e.prev = 0; e.has_prev = 0;
-            if (valid) {
-                const PTileEntry* te = PP.tiles + tile;
-                u32 flag = P_NOT_READY32;
-                for (int i = 0; i < P_POLLS; ++i) {  // the pre-pass may still be running (side stream)
-                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(&te->pad) : "memory");
-                    if (flag != P_NOT_READY32) break;
-                    __nanosleep(250);
-                }
-                if (flag != P_NOT_READY32) {
-                    __threadfence();
-                    const u64* w = reinterpret_cast<const u64*>(te);  // {task,list_first} {k,na} a0 plan_idx prev {has_prev,pad}
-                    const u64 w0 = ld_cg64(w), w1 = ld_cg64(w + 1), w5 = ld_cg64(w + 5);
-                    e.task = (u32)w0; e.list_first = (u32)(w0 >> 32); e.k = (u32)w1; e.na = (u32)(w1 >> 32);
-                    e.a0 = ld_cg64(w + 2); e.plan_idx = ld_cg64(w + 3); e.prev = ld_cg64(w + 4);
-                    e.has_prev = (u32)w5; e.pad = 0;
-                } else {
-                    e = tile_compute(P.tasks, P.lists, PP.plan_base, P.ntasks, tile);  // not there yet: do it here
-                }
-            }
+            if (valid) e = PP.tiles[tile];
             u64 r0 = 0, r1 = 0, lenj = 0;
             const u64* ptrj = nullptr;
             const u64* A = nullptr;
@@ -496,11 +438,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                     const FList Lj = P.lists[e.list_first + 1 + u];
                     ptrj = Lj.ptr;
                     lenj = flist_len(Lj);
-                    PPlanEntry pe;
-                    if (!plan_poll(PP.plan + e.plan_idx + u, pe)) {
-                        const FList LA = P.lists[e.list_first];
-                        pe = plan_compute(LA.ptr, flist_len(LA), e.a0, Lj.ptr, lenj);
-                    }
+                    const PPlanEntry pe = PP.plan[e.plan_idx + u];
                     r0 = pe.r0; r1 = pe.r1;
                 }
                 if (u == 0) A = P.lists[e.list_first].ptr;
@@ -866,11 +804,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                     const FList Lj = P.lists[G.list_first + 1 + t];
                     const u64* __restrict__ B = Lj.ptr;
                     const u64 lenB = flist_len(Lj);
-                    PPlanEntry e;
-                    if (!plan_poll(PP.plan + G.plan_idx + t, e)) {
-                        const FList LA = P.lists[G.list_first];
-                        e = plan_compute(LA.ptr, flist_len(LA), G.a0, B, lenB);
-                    }
+                    const PPlanEntry e = PP.plan[G.plan_idx + t];
                     const u64 sz = e.r1 - e.r0;
 #pragma unroll
                     for (int i = 0; i < P_VA; ++i) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-tools/ab.sh libdgx.so libdgx.so:DGX_PREPASS_OVERLAP=0 libdgx_hw.so libdgx_slp.so
-for T in 4 3 6; do
+tools/ab.sh libdgx.so libdgx.so:DGX_PREPASS_OVERLAP=0 libdgx_slp.so
+for T in 4; do
 timeout 120 python bench.py --steps 5 --warmup 3 --no-ops --no-dense --e2e-threads $T > gpurun_out/r2_bench6_$T.json 2> gpurun_out/r2_bench6_$T.err || { echo "T=$T FAILED rc=$?"; tail -3 gpurun_out/r2_bench6_$T.err; continue; }
 python - <<PY
 import json
