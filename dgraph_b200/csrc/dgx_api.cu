@@ -227,7 +227,8 @@ extern "C" int dgx_init(int device) {
                             (int)(sizeof(DWarpSmem) * D_WARPS)));
     CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * F_TA * sizeof(u64) + kScapMax)));
-    CK(cudaFuncSetAttribute(filter_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
+    CK(cudaFuncSetAttribute(filter_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
+    CK(cudaFuncSetAttribute(filter_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemMax));
     CK(cudaFuncSetAttribute(mmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * MM_CP * sizeof(u64))));
     g_num_sms = prop.multiProcessorCount;
     numa_probe(device);
@@ -436,7 +437,9 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     size_t li = 0, kmax = 1;
     for (size_t q = 0; q < nq; ++q) kmax = std::max(kmax, k_off[q + 1] - k_off[q]);
     const bool use_pipe = g_filter_pipe && kmax >= g_pipe_min_k;
-    const uint64_t tile_sz = use_pipe ? P_TA : F_TA;
+    // 2-list batches: 1024-value tiles (per-tile overheads over twice the values); wider queries: 512 (filter_pipe.cuh)
+    const int pipe_va = kmax <= 2 ? 4 : 2;
+    const uint64_t tile_sz = use_pipe ? (uint64_t)p_tile_size(pipe_va) : (uint64_t)F_TA;
     std::vector<size_t> order;
     for (size_t q = 0; q < nq; ++q) {
         const size_t k0 = k_off[q], k1 = k_off[q + 1];
@@ -511,7 +514,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         if (rc) return rc;
         CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, l->stream));
         filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
-                                                                                      P.ntiles, (PTileEntry*)d_tiles);
+                                                                                      P.ntiles, (PTileEntry*)d_tiles, (u32)tile_sz);
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;
@@ -519,7 +522,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
             const u64 blocks = (npairs + 255) / 256;
             if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
             filter_plan_kernel<<<(unsigned)blocks, 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
-                                                                         (PPlanEntry*)d_plan);
+                                                                         (PPlanEntry*)d_plan, (u32)tile_sz);
             CK(cudaGetLastError());
             l->launches += 1;
             g_stats.launches += 1;
@@ -533,19 +536,23 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         // C2); 2-list batches have tiny tiles and amortise the metadata chain over two (measured +4 %)
         PP.grp = kmax >= 4 ? 1u : 2u;
         const size_t nl = std::min<size_t>(std::max<size_t>(kmax - 1, 1), P_MAXL);
-        size_t cap = (P_TA + P_TA / 8) * nl * (kmax <= 2 ? 4 : 1);
+        const size_t TA = (size_t)tile_sz;
+        // staged slices: ~1.125 tile-widths per filter list; a 2-list batch stages up to 2.25 tile-widths of its one
+        // filter list (size ratios beyond that probe the list in HBM, the reference's own Jump / Bin regimes)
+        size_t cap = (TA + TA / 8) * nl * (kmax <= 2 ? 2 : 1);
         if (g_scap_override) cap = g_scap_override / 8;
-        cap = std::min<size_t>(std::max<size_t>(cap, P_TA + P_TA / 8), 9216) & ~size_t(1);
+        cap = std::min<size_t>(std::max<size_t>(cap, TA + TA / 8), 9216) & ~size_t(1);
         PP.slice_cap = (u32)cap;
-        const size_t smem = ((sizeof(PShared) + 127) & ~size_t(127)) + (1 + P_OS) * P_TA * sizeof(u64) +
-                            P_ST * ((P_TA + 2) + cap) * sizeof(u64);
+        const size_t smem = ((sizeof(PShared) + 127) & ~size_t(127)) + (1 + P_OS) * TA * sizeof(u64) +
+                            P_ST * ((TA + 2) + cap) * sizeof(u64);
         if (smem > kPipeSmemMax) return fail(DGX_ERR_ARG, "pipeline stage too large");
+        auto kern = pipe_va == 4 ? filter_pipe_kernel<4> : filter_pipe_kernel<2>;
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pipe_kernel, P_NT, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P_NT, smem));
         if (per_sm < 1) return fail(DGX_ERR_CUDA, "filter_pipe_kernel does not fit on an SM");
         const u64 resident = (u64)per_sm * (u64)g_num_sms;
         PP.nctas = (u32)std::min<u64>(resident, ntiles);
-        filter_pipe_kernel<<<PP.nctas, P_NT, smem, l->stream>>>(PP);
+        kern<<<PP.nctas, P_NT, smem, l->stream>>>(PP);
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;

@@ -37,16 +37,19 @@
 
 namespace dgx {
 
-#ifndef DGX_P_VA
-#define DGX_P_VA 2
-#endif
-constexpr int P_VA = DGX_P_VA;           // candidate rows per consumer warp (2 or 4)
-constexpr int P_WC = 32 * P_VA;          // candidates per consumer warp
-constexpr int P_TA = 512;                // candidates per tile
-constexpr int P_CW = P_TA / P_WC;        // consumer warps
+// Tile geometry is a template parameter of the kernel: VA candidate rows per consumer warp, 32 VA candidates per
+// warp, 8 consumer warps, 256 VA candidates per tile.  Wide queries (k >= 3) run VA = 2 (512-value tiles: more
+// tiles in flight per byte of shared memory, measured best on C2); 2-list batches run VA = 4 (1024-value tiles:
+// their per-tile costs -- metadata, TMA issue, look-back, delivery -- are spread over twice the values).
+constexpr int P_CW = 8;                  // consumer warps
 constexpr int P_CT = P_CW * 32;          // consumer threads
 constexpr int P_NT = P_CT + 96;          // + metadata warp + TMA warp + output warp
-static_assert(P_VA == 2 || P_VA == 4, "rows per consumer warp");
+#define DGX_GEOM(VA)                                                                     \
+    constexpr int P_VA = (VA);           /* candidate rows per consumer warp */           \
+    constexpr int P_WC = 32 * (VA);      /* candidates per consumer warp */               \
+    constexpr int P_TA = P_CW * 32 * (VA); /* candidates per tile */                      \
+    static_assert(P_VA == 2 || P_VA == 4, "rows per consumer warp")
+constexpr int p_tile_size(int va) { return P_CW * 32 * va; }
 #ifndef DGX_P_OS
 #define DGX_P_OS 6
 #endif
@@ -74,7 +77,6 @@ constexpr u32 P_END = 0xffffffffu;
 #ifndef DGX_P_SLEEP_LB
 #define DGX_P_SLEEP_LB 1000
 #endif
-static_assert(P_CW * P_WC == P_TA, "tile geometry");
 
 struct PPlanEntry { u64 r0, r1; };
 struct PTileEntry {            // everything the metadata warp needs about a tile, resolved by filter_tiles_kernel
@@ -100,7 +102,7 @@ struct PParams {
 // search of filter_kernel.cuh touches ~70: the plan must not cost a second pass over HBM.
 __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
                                                           const u64* __restrict__ plan_base, u32 ntasks, u64 npairs,
-                                                          PPlanEntry* __restrict__ plan) {
+                                                          PPlanEntry* __restrict__ plan, u32 tile_sz) {
     const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     u32 lo = 0, hi = ntasks;  // last task with plan_base <= p (the one that owns pair p)
@@ -115,10 +117,10 @@ __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restric
     const u32 j = (u32)(local - tl * km1) + 1;
     const FList LA = lists[T.list_first];
     const u64 lenA = flist_len(LA);
-    const u64 a0 = tl * P_TA;
+    const u64 a0 = tl * (u64)tile_sz;
     u64 r0 = 0, r1 = 0;
     if (a0 < lenA) {
-        const u64 na = lenA - a0 < (u64)P_TA ? lenA - a0 : (u64)P_TA;
+        const u64 na = lenA - a0 < (u64)tile_sz ? lenA - a0 : (u64)tile_sz;
         const u64 tlo = ld_probe(LA.ptr + a0), thi = ld_probe(LA.ptr + a0 + na - 1);
         const FList Lj = lists[T.list_first + j];
         const u64* __restrict__ B = Lj.ptr;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restric
 // One thread per tile: which task it belongs to and where its driving values start.
 __global__ void __launch_bounds__(256) filter_tiles_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
                                                            const u64* __restrict__ plan_base, u32 ntasks, u32 ntiles,
-                                                           PTileEntry* __restrict__ tiles) {
+                                                           PTileEntry* __restrict__ tiles, u32 tile_sz) {
     const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= ntiles) return;
     u32 lo = 0, hi = ntasks;
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(256) filter_tiles_kernel(const FTask* __restri
     const u64 lenA = flist_len(LA);
     PTileEntry e;
     e.task = lo; e.list_first = T.list_first; e.k = T.k;
-    e.a0 = ((u64)tile - T.tile_base) * P_TA;
-    e.na = e.a0 < lenA ? (u32)((lenA - e.a0 < (u64)P_TA) ? (lenA - e.a0) : (u64)P_TA) : 0u;
+    e.a0 = ((u64)tile - T.tile_base) * (u64)tile_sz;
+    e.na = e.a0 < lenA ? (u32)((lenA - e.a0 < (u64)tile_sz) ? (lenA - e.a0) : (u64)tile_sz) : 0u;
     e.plan_idx = plan_base[lo] + ((u64)tile - T.tile_base) * (u64)(T.k - 1);
     e.has_prev = (e.a0 > 0 && e.na > 0) ? 1u : 0u;
     e.prev = e.has_prev ? ld_probe(LA.ptr + e.a0 - 1) : 0;
@@ -195,6 +197,7 @@ __device__ __forceinline__ void mbar_arrive(u32 bar) {
 }
 
 // Re-pack a consumer warp's survivors into rows 0..ceil(live/32)-1 (order preserved).
+template <int P_VA>
 __device__ __forceinline__ void pwarp_repack(u64 (&c)[P_VA], unsigned& alive, int& rows, u64* s_w, int lane) {
     unsigned b[P_VA];
     int tot = 0;
@@ -379,7 +382,9 @@ __device__ unsigned long long g_pprof[32];
 #define PPROF_PHASE_FLUSH()
 #endif
 
+template <int VA>
 __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) {
+    DGX_GEOM(VA);
     extern __shared__ __align__(128) unsigned char p_smem[];
     const FParams& P = PP.f;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -819,7 +824,7 @@ __global__ void __launch_bounds__(P_NT, 2) filter_pipe_kernel(const PParams PP) 
                     t += 1;
                 }
                 if (t < km1) {
-                    if (!warp_dup) pwarp_repack(c, alive, rows, s_w, lane);
+                    if (!warp_dup) pwarp_repack<P_VA>(c, alive, rows, s_w, lane);
                     else if (!__any_sync(0xffffffffu, alive != 0)) rows = 0;
                 }
             }

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/r2_ref.json 2> gpurun_out/r2_ref.err; tail -c 700 gpurun_out/r2_ref.json; echo
+timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench7.json 2> gpurun_out/r2_bench7.err; echo "bench rc=$?"; tail -3 gpurun_out/r2_bench7.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2_bench7.json").read().strip().splitlines()[-1])
+print("value %.4g ms %.4f frac %.3f exact %s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["bit_exact"]))
+print("dense", d["dense_variant"])
+for k in ("e2e","e2e_cached","e2e_raw_u64"): print(k, round(d[k]["ms_per_step"],3), "%.4g"%d[k]["value"], d[k].get("pcie_GBps"), d[k]["bit_exact"])
+for r in d["ops"]: print(r["op"], "|", r["ms"], "ms |", r["frac_of_hbm_peak"], r["check"])
+print("cpu", d["cpu_baseline"]["value"])
+PY
