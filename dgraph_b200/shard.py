@@ -112,6 +112,11 @@ def gatherv_exact(dist, parts, local_out, local_off, device=None):
     np.cumsum(lens_g, out=off_host[1:])
     base = np.concatenate([[0], np.cumsum(tot)]).astype(np.int64)
     out_g = torch.empty(max(int(base[-1]), 1), dtype=torch.int64, device=dev)
+    if dist.get_backend() == "nccl" and all(t > 0 for t in tot):
+        # NCCL's all_gather takes outputs of different sizes (one grouped broadcast per rank, ring / NVLS
+        # bandwidth): every shard lands in its final place
+        dist.all_gather([out_g[int(base[r]): int(base[r]) + tot[r]] for r in range(world)], local_out[: tot[rank]])
+        return out_g[: int(base[-1])], torch.from_numpy(off_host).to(dev)
     ops = []
     for r in range(world):
         if r == rank:
