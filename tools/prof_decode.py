@@ -6,15 +6,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import bench_ops as B
 from dgraph_b200 import _lib
-from oracle import pyoracle as orc
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gen as hostgen
 L = B.Lane()
 gen = torch.Generator(device=B.DEV); gen.manual_seed(5)
 n3 = int(sys.argv[1]) if len(sys.argv) > 1 else 25_000_000
 master = B.zipf_gaps_gpu(n3, gen)
 host = master.cpu().numpy().view(np.uint64)
-pack = orc.encode(host, 256)
+_, base, num, doff_, deltas = hostgen.encode_pack_np_parallel(host, 256)
+class _P: pass
+pack = _P(); pack.nblocks = base.size
 view = _lib.PackView()
-base, num, doff_, deltas = pack.base, pack.num_uids, pack.delta_off, pack.deltas
 view.block_size, view.nblocks = 256, pack.nblocks
 view.base, view.num_uids, view.delta_off, view.deltas = base.ctypes.data, num.ctypes.data, doff_.ctypes.data, deltas.ctypes.data
 pk = C.c_void_p()
