@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -71,6 +72,9 @@ static Stats g_stats;
 static std::mutex g_mu;
 static int g_device = -1;
 static std::vector<dgx_lane*> g_pool;  // idle lanes for the host-pointer entry points
+static std::condition_variable g_pool_cv;
+static size_t g_lanes_out = 0;     // lanes currently leased
+static size_t g_lanes_total = 0;   // lanes in existence (pooled + leased)
 static u32 g_stream_ratio = 16;
 static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's slice staging capacity
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
@@ -243,9 +247,11 @@ extern "C" int dgx_init(int device) {
 
 extern "C" void dgx_shutdown(void) {
     dgx_cache_clear();
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::mutex> lk(g_mu);
+    g_pool_cv.wait(lk, [] { return g_lanes_out == 0; });  // calls in flight keep their lanes until they return
     for (dgx_lane* l : g_pool) dgx_lane_destroy(l);
     g_pool.clear();
+    g_lanes_total = 0;
     g_device = -1;
 }
 
@@ -1161,26 +1167,50 @@ extern "C" int dgx_dev_decode(dgx_lane* l, const dgx_dev_pack* pk, uint64_t seek
 // ---------------------------------------------------------------------------
 // host-pointer entry points
 // ---------------------------------------------------------------------------
+// Lanes of the host-pointer entry points.  The pool is bounded: at most kMaxLanes lanes exist (each keeps a stream,
+// its workspace and pinned staging at their high-water mark), a caller beyond that waits for one to come back --
+// hundreds of cgo goroutines cannot pin hundreds of arenas in HBM.  A lane whose workspace grew past kLaneTrimBytes is
+// shrunk when it is returned (it is idle then: every host-pointer call ends with a stream sync).
+constexpr size_t kMaxLanes = 32;
+constexpr size_t kLaneTrimBytes = size_t(4) << 30;
 struct LaneLease {
     dgx_lane* l = nullptr;
     int rc = DGX_OK;
     LaneLease() {
         rc = dgx_init(-1);
         if (rc) return;
+        bool create = false;
         {
-            std::lock_guard<std::mutex> lk(g_mu);
+            std::unique_lock<std::mutex> lk(g_mu);
+            g_pool_cv.wait(lk, [] { return !g_pool.empty() || g_lanes_total < kMaxLanes; });
             if (!g_pool.empty()) { l = g_pool.back(); g_pool.pop_back(); }
+            else { create = true; g_lanes_total += 1; }
+            g_lanes_out += 1;
         }
-        if (!l) {
+        if (create) {
             l = dgx_lane_create(g_device, nullptr);
-            if (!l) rc = fail(DGX_ERR_CUDA, "cannot create lane: %s", g_err.c_str());
+            if (!l) {
+                rc = fail(DGX_ERR_CUDA, "cannot create lane: %s", g_err.c_str());
+                std::lock_guard<std::mutex> lk(g_mu);
+                g_lanes_total -= 1;
+                g_lanes_out -= 1;
+                g_pool_cv.notify_all();
+                return;
+            }
         }
-        if (l) { cudaSetDevice(l->device); l->ws.reset(); }
+        cudaSetDevice(l->device);
+        l->ws.reset();
     }
     ~LaneLease() {
         if (!l) return;
+        if (l->ws.cap > kLaneTrimBytes) {  // idle (synchronised) lane: give a one-off large workspace back
+            cudaStreamSynchronize(l->stream);
+            l->ws.destroy();
+        }
         std::lock_guard<std::mutex> lk(g_mu);
         g_pool.push_back(l);
+        g_lanes_out -= 1;
+        g_pool_cv.notify_all();
     }
 };
 
