@@ -83,6 +83,7 @@ static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise mer
 static u32 g_merge_stride = 6;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values of a 4096 chunk)
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
+static uint64_t g_pipe_min_values = 0;  // DGX_PIPE_MIN_VALUES: batches driving fewer values than this use filter_kernel
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
 static int g_num_sms = 148;
 constexpr size_t kPipeSmemMax = 220 * 1024;
@@ -444,7 +445,16 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     uint64_t ntiles = 0, uids_in = 0;
     size_t li = 0, kmax = 1;
     for (size_t q = 0; q < nq; ++q) kmax = std::max(kmax, k_off[q + 1] - k_off[q]);
-    const bool use_pipe = g_filter_pipe && kmax >= g_pipe_min_k;
+    // Small batches take the single-launch kernel: the pipeline's plan pre-pass (two more launches, a second
+    // descriptor copy) costs more than it saves when the whole batch is a few hundred tiles (DGX_PIPE_MIN_VALUES).
+    uint64_t drive_total = 0;
+    for (size_t q = 0; q < nq; ++q) {
+        uint64_t mn = UINT64_MAX;
+        for (size_t i = k_off[q]; i < k_off[q + 1]; ++i) mn = std::min<uint64_t>(mn, lists[i].len);
+        if (op == DGX_OP_DIFFERENCE && k_off[q + 1] > k_off[q]) mn = lists[k_off[q]].len;
+        if (mn != UINT64_MAX) drive_total += mn;
+    }
+    const bool use_pipe = g_filter_pipe && kmax >= g_pipe_min_k && drive_total >= g_pipe_min_values;
     // 2-list batches: 1024-value tiles (per-tile overheads over twice the values); wider queries: 512 (filter_pipe.cuh)
     const int pipe_va = kmax <= 2 ? 4 : 2;
     const uint64_t tile_sz = use_pipe ? (uint64_t)p_tile_size(pipe_va) : (uint64_t)F_TA;

@@ -33,6 +33,14 @@ def main():
         for _ in range(int(os.environ.get("PAIRS", "2048"))):
             queries.append([np.unique(rng.integers(0, 10_000_000, 102_000, dtype=np.uint64))[:100_000].copy() for _ in range(2)])
         Q = len(queries)
+    elif os.environ.get("WORKLOAD") == "c4":  # C4 shape: 2-way pairs, thinnings p = 0.5 of a per-pair master (half of A survives)
+        rng = np.random.default_rng(9)
+        queries = []
+        for _ in range(int(os.environ.get("PAIRS", "512"))):
+            n = int(rng.integers(20_000, 400_000))
+            master = np.cumsum(np.minimum(rng.zipf(1.5, 2 * n), 1 << 20).astype(np.uint64), dtype=np.uint64)
+            queries.append([master[rng.random(master.size) < 0.5] for _ in range(2)])
+        Q = len(queries)
     else:
         queries = bench.make_queries(Q, 0)
     dev = torch.device("cuda", 0)
