@@ -497,3 +497,46 @@ def test_packed_ops_random(dgx, orc):
     same_pack(dgx.algo.IntersectWithLinPacked(packs[0], None), orc.encode(np.zeros(0, np.uint64), 256), "nil operand")
     same_pack(dgx.algo.DifferencePacked(packs[0], None), orc.encode(lists[0], 256), "minus nil")
     same_pack(dgx.algo.MergeSortedPacked([None, packs[3], None]), orc.encode(lists[3], 256), "merge with nils")
+
+
+# ---- filter_pipe 32-bit fast path: geometry stress ------------------------------------------------------------
+
+def test_filter_fast_path_stress(dgx, orc):
+    """Many small random queries aimed at the fast path's corners: slice lengths around powers of two and far apart
+    (one ladder for several lists needs P <= n <= 3P), empty slices in the middle of a chain, tiles that straddle a
+    multiple of 2^32 (must fall back to 64-bit searches), single-row and multi-row warps, Difference, both tile
+    geometries (k = 2 -> 1024-value tiles, k >= 3 -> 512)."""
+    rng = np.random.default_rng(60)
+    bases = [0, (1 << 32) - 40_000, (1 << 32) - 300, (7 << 32) + 123, (1 << 63) + 17, (1 << 64) - 2_000_000]
+    for it in range(160):
+        base = bases[it % len(bases)]
+        k = int(rng.integers(2, 10))
+        span = int(rng.choice([3_000, 40_000, 600_000]))
+        master = np.unique(rng.integers(0, span, int(rng.integers(50, 9000)), dtype=np.uint64)) + np.uint64(base)
+        lists = []
+        for j in range(k):
+            p = float(rng.choice([0.02, 0.2, 0.5, 0.9, 1.0]))
+            l = master[rng.random(master.size) < p]
+            if rng.random() < 0.15:        # a list that misses a whole stretch: empty slices for some tiles
+                cut = master[master.size // 3], master[2 * master.size // 3]
+                l = l[(l < cut[0]) | (l > cut[1])]
+            if rng.random() < 0.1:         # a much longer list (different ladder length than its neighbours)
+                l = np.unique(np.concatenate([l, rng.integers(0, span, 20_000, dtype=np.uint64) + np.uint64(base)]))
+            lists.append(l)
+        got = dgx.algo.IntersectSorted([L(dgx, l) for l in lists])
+        eq(got.Uids, orc.intersect_sorted(lists), f"stress {it} k={k} base={base:#x}")
+        d = dgx.algo.Difference(L(dgx, lists[0]), L(dgx, lists[1]))
+        eq(d.Uids, orc.difference(lists[0], lists[1]), f"stress diff {it}")
+    # one batch mixing widths (the batch runs the geometry of its widest query)
+    rows_a, rows_b = [], []
+    for it in range(40):
+        m = np.unique(rng.integers(0, 1 << 20, int(rng.integers(0, 5000)), dtype=np.uint64)) + np.uint64(bases[it % 4])
+        rows_a.append(m[rng.random(m.size) < 0.6])
+        rows_b.append(m[rng.random(m.size) < 0.4])
+    a = np.concatenate(rows_a + [np.zeros(0, np.uint64)])
+    b = np.concatenate(rows_b + [np.zeros(0, np.uint64)])
+    a_off = np.concatenate([[0], np.cumsum([r.size for r in rows_a])]).astype(np.uint64)
+    b_off = np.concatenate([[0], np.cumsum([r.size for r in rows_b])]).astype(np.uint64)
+    out, off = dgx.algo.IntersectBatch(a, a_off, b, b_off)
+    for i in range(40):
+        eq(out[int(off[i]): int(off[i + 1])], orc.intersect_with(rows_a[i], rows_b[i]), f"batch row {i}")
