@@ -14,6 +14,7 @@ GPU box).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
@@ -112,21 +113,20 @@ def gatherv_exact(dist, parts, local_out, local_off, device=None):
     np.cumsum(lens_g, out=off_host[1:])
     base = np.concatenate([[0], np.cumsum(tot)]).astype(np.int64)
     out_g = torch.empty(max(int(base[-1]), 1), dtype=torch.int64, device=dev)
-    if dist.get_backend() == "nccl" and all(t > 0 for t in tot):
-        # NCCL's all_gather takes outputs of different sizes (one grouped broadcast per rank, ring / NVLS
-        # bandwidth): every shard lands in its final place
-        dist.all_gather([out_g[int(base[r]): int(base[r]) + tot[r]] for r in range(world)], local_out[: tot[rank]])
-        return out_g[: int(base[-1])], torch.from_numpy(off_host).to(dev)
+    # grouped point-to-point transfers of the exact sizes (ncclGroupStart/End under NCCL), one per peer.  Measured on
+    # 2 GPUs, 0.96 GB per peer: 3.9 ms this way; cut into 8 or 64 MiB pieces 8.4 ms; NCCL's uneven all_gather (one
+    # broadcast per rank) 6.5 ms.
+    piece = int(os.environ.get("DGX_GATHER_PIECE", str(1 << 40)))  # values per transfer (default: one per peer)
     ops = []
     for r in range(world):
         if r == rank:
             if tot[r]:
                 out_g[int(base[r]): int(base[r]) + tot[r]].copy_(local_out[: tot[r]])
             continue
-        if tot[rank]:
-            ops.append(dist.P2POp(dist.isend, local_out[: tot[rank]], r))
-        if tot[r]:
-            ops.append(dist.P2POp(dist.irecv, out_g[int(base[r]): int(base[r]) + tot[r]], r))
+        for o in range(0, tot[rank], piece):
+            ops.append(dist.P2POp(dist.isend, local_out[o: min(o + piece, tot[rank])], r))
+        for o in range(0, tot[r], piece):
+            ops.append(dist.P2POp(dist.irecv, out_g[int(base[r]) + o: int(base[r]) + min(o + piece, tot[r])], r))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
