@@ -83,6 +83,7 @@ static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise mer
 static u32 g_merge_stride = 6;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values of a 4096 chunk)
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
+static u32 g_reserve_ctas = 0;         // DGX_RESERVE_CTAS: pipeline CTAs left out of the persistent grid
 static uint64_t g_pipe_min_values = 0;  // DGX_PIPE_MIN_VALUES: batches driving fewer values than this use filter_kernel
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
 static int g_num_sms = 148;
@@ -568,7 +569,10 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P_NT, smem));
         if (per_sm < 1) return fail(DGX_ERR_CUDA, "filter_pipe_kernel does not fit on an SM");
-        const u64 resident = (u64)per_sm * (u64)g_num_sms;
+        u64 resident = (u64)per_sm * (u64)g_num_sms;
+        // DGX_RESERVE_CTAS: leave a few CTA slots free so that a collective queued on another stream (the result
+        // gather of the previous batch) finds an SM while the persistent pipeline runs
+        if (g_reserve_ctas && resident > 2 * (u64)g_reserve_ctas) resident -= g_reserve_ctas;
         PP.nctas = (u32)std::min<u64>(resident, ntiles);
         kern<<<PP.nctas, P_NT, smem, l->stream>>>(PP);
         CK(cudaGetLastError());
