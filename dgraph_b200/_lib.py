@@ -87,6 +87,7 @@ SYMBOLS = {
     "dgx_lane_destroy": (None, [_vp]),
     "dgx_lane_sync": (_int, [_vp]),
     "dgx_lane_stream": (_vp, [_vp]),
+    "dgx_lane_set_resident_inputs": (_int, [_vp, _int]),
     "dgx_lane_launches": (_u64, [_vp]),
     "dgx_dev_alloc": (_vp, [_sz]),
     "dgx_dev_free": (None, [_vp]),

@@ -188,6 +188,13 @@ struct dgx_lane {
     uint64_t* h_word = nullptr;  // pinned scratch for lengths (8 words)
     uint64_t* h_head = nullptr;  // pinned landing zone for the head of a result (kSpecHead values)
     uint64_t launches = 0;
+    // "resident lists" mode (dgx_lane_set_resident_inputs): the plan pre-pass of batch i+1 runs on a side stream while
+    // the pipeline kernel of batch i is still running; its tables live in two alternating workspaces
+    bool resident_inputs = false;
+    cudaStream_t side = nullptr;
+    DevArena fws[2];
+    cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_pipe[2] = {nullptr, nullptr};
+    int fslot = 0;
 };
 // Results up to this many values reach the host in the same round trip as their length.
 constexpr size_t kSpecHead = 8192;
@@ -374,11 +381,32 @@ extern "C" void dgx_lane_destroy(dgx_lane* l) {
     l->host.destroy();
     if (l->d_err) cudaFree(l->d_err);
     if (l->h_err) cudaFreeHost(l->h_err);
+    if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
+    for (int i = 0; i < 2; ++i) {
+        l->fws[i].destroy();
+        if (l->ev_plan[i]) cudaEventDestroy(l->ev_plan[i]);
+        if (l->ev_pipe[i]) cudaEventDestroy(l->ev_pipe[i]);
+    }
     if (l->own_stream) cudaStreamDestroy(l->stream);
     delete l;
 }
 
 extern "C" void* dgx_lane_stream(dgx_lane* l) { return l ? (void*)l->stream : nullptr; }
+
+extern "C" int dgx_lane_set_resident_inputs(dgx_lane* l, int on) {
+    if (!l) return fail(DGX_ERR_ARG, "null lane");
+    CK(cudaSetDevice(l->device));
+    if (on && !l->side) {
+        CK(cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&l->ev_plan[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&l->ev_pipe[i], cudaEventDisableTiming));
+        }
+    }
+    if (!on && l->side) CK(cudaStreamSynchronize(l->side));
+    l->resident_inputs = on != 0;
+    return DGX_OK;
+}
 extern "C" uint64_t dgx_lane_launches(const dgx_lane* l) { return l ? l->launches : 0; }
 
 extern "C" int dgx_lane_sync(dgx_lane* l) {
@@ -486,11 +514,26 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
     }
     if (ntiles > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large (%llu tiles)", (unsigned long long)ntiles);
     const size_t status_b = ntiles * sizeof(u64) + 64;
-    rc = l->ws.alloc(tasks_b + lists_b + status_b, &d_raw);
+    // Where the batch's tables live and which stream prepares them.  Normally: the lane's workspace and stream.
+    // Resident-inputs lanes: one of two alternating workspaces and the side stream -- descriptor copies, status
+    // reset and the plan pre-pass of THIS batch then run while the pipeline kernel of the PREVIOUS batch is still
+    // busy (the lists are immutable, so the pre-pass depends on nothing the main stream has queued).
+    const bool ahead = l->resident_inputs && use_pipe && l->side;
+    const int slot = l->fslot;
+    DevArena* ar = &l->ws;
+    cudaStream_t pre = l->stream;
+    if (ahead) {
+        l->fslot ^= 1;
+        ar = &l->fws[slot];
+        pre = l->side;
+        CK(cudaStreamWaitEvent(l->side, l->ev_pipe[slot], 0));  // the pipeline that last read this workspace is done
+        ar->reset();
+    }
+    rc = ar->alloc(tasks_b + lists_b + status_b, &d_raw);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(d_raw, h_raw, tasks_b + lists_b, cudaMemcpyHostToDevice, l->stream));
+    CK(cudaMemcpyAsync(d_raw, h_raw, tasks_b + lists_b, cudaMemcpyHostToDevice, pre));
     char* d_status = (char*)d_raw + tasks_b + lists_b;
-    CK(cudaMemsetAsync(d_status, 0, status_b, l->stream));
+    CK(cudaMemsetAsync(d_status, 0, status_b, pre));
     FParams P;
     P.tasks = (const FTask*)d_raw;
     P.lists = (const FList*)((char*)d_raw + tasks_b);
@@ -525,14 +568,14 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
             npairs += nt * (u64)(ht[q].k - 1);
         }
         void *d_pb, *d_plan, *d_tiles;
-        rc = l->ws.alloc(nq * sizeof(u64), &d_pb);
+        rc = ar->alloc(nq * sizeof(u64), &d_pb);
         if (rc) return rc;
-        rc = l->ws.alloc(ntiles * sizeof(PTileEntry), &d_tiles);
+        rc = ar->alloc(ntiles * sizeof(PTileEntry), &d_tiles);
         if (rc) return rc;
-        rc = l->ws.alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
+        rc = ar->alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, l->stream));
-        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
+        CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, pre));
+        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
                                                                                       P.ntiles, (PTileEntry*)d_tiles, (u32)tile_sz);
         CK(cudaGetLastError());
         l->launches += 1;
@@ -540,7 +583,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         if (npairs) {
             const u64 blocks = (npairs + 255) / 256;
             if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
-            filter_plan_kernel<<<(unsigned)blocks, 256, 0, l->stream>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
+            filter_plan_kernel<<<(unsigned)blocks, 256, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
                                                                          (PPlanEntry*)d_plan, (u32)tile_sz);
             CK(cudaGetLastError());
             l->launches += 1;
@@ -574,10 +617,15 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         // gather of the previous batch) finds an SM while the persistent pipeline runs
         if (g_reserve_ctas && resident > 2 * (u64)g_reserve_ctas) resident -= g_reserve_ctas;
         PP.nctas = (u32)std::min<u64>(resident, ntiles);
+        if (ahead) {
+            CK(cudaEventRecord(l->ev_plan[slot], l->side));
+            CK(cudaStreamWaitEvent(l->stream, l->ev_plan[slot], 0));
+        }
         kern<<<PP.nctas, P_NT, smem, l->stream>>>(PP);
         CK(cudaGetLastError());
         l->launches += 1;
         g_stats.launches += 1;
+        if (ahead) CK(cudaEventRecord(l->ev_pipe[slot], l->stream));
     }
     g_stats.uids_in += uids_in;
     return DGX_OK;

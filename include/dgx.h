@@ -293,6 +293,12 @@ dgx_lane* dgx_lane_create(int device, void* stream);
 void dgx_lane_destroy(dgx_lane* lane);
 int dgx_lane_sync(dgx_lane* lane);
 void* dgx_lane_stream(dgx_lane* lane);
+/* Declare that the device lists passed to dgx_dev_filter_batch on this lane are RESIDENT: complete before the call
+ * and not written by anything queued on the lane's stream (the contract of a pack / list cache: posting lists are
+ * immutable once rolled up).  The plan pre-pass of a batch then runs on a side stream while the pipeline kernel of the
+ * previous batch is still busy (its tables alternate between two workspaces).  Results (d_out, d_out_off) stay ordered
+ * on the lane's stream as before.  Off by default; the host-pointer entry points never use it. */
+int dgx_lane_set_resident_inputs(dgx_lane* lane, int on);
 /* Number of kernels this lane has launched so far. */
 uint64_t dgx_lane_launches(const dgx_lane* lane);
 

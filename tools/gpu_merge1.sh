@@ -1,2 +1,2 @@
 #!/bin/bash
-for st in 4 5 6; do echo "stride $st"; CHECK=1 DGX_MERGE_STRIDE=$st timeout 120 python tools/prof_merge.py 100000000 2>&1 | tail -2; done
+for st in 6 7; do echo "stride $st"; CHECK=1 DGX_MERGE_STRIDE=$st timeout 120 python tools/prof_merge.py 100000000 2>&1 | tail -2; done
