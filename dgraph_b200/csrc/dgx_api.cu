@@ -83,6 +83,7 @@ static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise mer
 static u32 g_merge_stride = 6;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values of a 4096 chunk)
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
+static size_t g_pre_throttle_smem = 0;  // DGX_PRE_THROTTLE: dynamic smem asked for by an ahead-of-time pre-pass (0 = unthrottled)
 static u32 g_reserve_ctas = 0;         // DGX_RESERVE_CTAS: pipeline CTAs left out of the persistent grid
 static uint64_t g_pipe_min_values = 0;  // DGX_PIPE_MIN_VALUES: batches driving fewer values than this use filter_kernel
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
@@ -575,7 +576,11 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         rc = ar->alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
         if (rc) return rc;
         CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, pre));
-        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
+        // DGX_PRE_THROTTLE: dynamic shared memory an ahead-of-time pre-pass asks for (16 KB would limit it to one CTA on
+        // an SM that holds two pipeline CTAs).  Measured: no effect (0.3559 vs 0.3565 ms) -- what the overlap costs the
+        // pipeline is L2 / DRAM interference, not issue slots -- so the default is 0.
+        const size_t pre_smem = ahead ? g_pre_throttle_smem : 0;
+        filter_tiles_kernel<<<(unsigned)((ntiles + 255) / 256), 256, pre_smem, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks,
                                                                                       P.ntiles, (PTileEntry*)d_tiles, (u32)tile_sz);
         CK(cudaGetLastError());
         l->launches += 1;
@@ -583,7 +588,7 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         if (npairs) {
             const u64 blocks = (npairs + 255) / 256;
             if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
-            filter_plan_kernel<<<(unsigned)blocks, 256, 0, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
+            filter_plan_kernel<<<(unsigned)blocks, 256, pre_smem, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
                                                                          (PPlanEntry*)d_plan, (u32)tile_sz);
             CK(cudaGetLastError());
             l->launches += 1;
