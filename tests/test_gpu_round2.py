@@ -540,3 +540,68 @@ def test_filter_fast_path_stress(dgx, orc):
     out, off = dgx.algo.IntersectBatch(a, a_off, b, b_off)
     for i in range(40):
         eq(out[int(off[i]): int(off[i + 1])], orc.intersect_with(rows_a[i], rows_b[i]), f"batch row {i}")
+
+
+# ---- resident-inputs lanes: the pre-pass of batch i+1 under the pipeline kernel of batch i -------------------------
+
+def test_resident_lane_batches(dgx, orc):
+    """dgx_lane_set_resident_inputs: batches queued back to back on one lane (their plan pre-pass -- the boundary-sharing
+    kernel -- runs ahead on a side stream, tables alternate between two workspaces).  Every batch is checked against the
+    oracle: wide queries, 2-list batches, Difference, duplicates repeated across tile boundaries, empty lists."""
+    import torch
+    from dgraph_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        lane = lib.dgx_lane_create(0, C.c_void_p(stream.cuda_stream))
+        assert lane
+        _lib.check(lib.dgx_lane_set_resident_inputs(lane, 1))
+        rng = np.random.default_rng(70)
+        master = gen.zipf_gaps(rng, 700_000)
+        dups = np.sort(rng.integers(0, 3000, 200_000, dtype=np.uint64))          # long runs of equal values
+        batches = []
+        for b in range(9):
+            op = 1 if b % 4 == 3 else 0
+            qs = []
+            for q in range(int(rng.integers(1, 6))):
+                if op == 1:
+                    k = 2
+                elif b % 3 == 0:
+                    k = 2
+                else:
+                    k = int(rng.integers(3, 9))
+                if b == 5:
+                    src = dups
+                    lists = [src[rng.random(src.size) < float(rng.choice([0.3, 0.7]))] for _ in range(k)]
+                else:
+                    lists = [gen.thin(rng, master, float(rng.choice([0.02, 0.3, 0.9]))) for _ in range(k)]
+                if b == 7 and q == 0:
+                    lists[1] = np.zeros(0, np.uint64)
+                qs.append(lists)
+            batches.append((op, qs))
+        # everything resident BEFORE the first call
+        dev_lists = [[[torch.from_numpy(l.view(np.int64).copy()).to(dev) for l in lists] for lists in qs] for _, qs in batches]
+        outs = []
+        for (op, qs), dls in zip(batches, dev_lists):
+            cap = sum((lists[0].size if op == 1 else min(l.size for l in lists)) for lists in qs)
+            outs.append((torch.empty(cap + 8, dtype=torch.int64, device=dev), torch.zeros(len(qs) + 1, dtype=torch.int64, device=dev), cap))
+        torch.cuda.synchronize()
+        for rep in range(3):                                                      # back to back, no sync in between
+            for (op, qs), dls, (o, off, cap) in zip(batches, dev_lists, outs):
+                flat = [t for lists in dls for t in lists]
+                koff = np.concatenate([[0], np.cumsum([len(l) for l in dls])])
+                ptrs = (C.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+                lens = (C.c_size_t * len(flat))(*[t.numel() for t in flat])
+                ck = (C.c_size_t * len(koff))(*[int(x) for x in koff])
+                _lib.check(lib.dgx_dev_filter_batch(lane, op, ptrs, lens, ck, len(qs), C.c_void_p(o.data_ptr()), cap,
+                                                    C.c_void_p(off.data_ptr())))
+        _lib.check(lib.dgx_lane_sync(lane))
+        for bi, ((op, qs), (o, off, cap)) in enumerate(zip(batches, outs)):
+            ho, hoff = o.cpu().numpy().view(np.uint64), off.cpu().numpy()
+            for qi, lists in enumerate(qs):
+                want = orc.difference(lists[0], lists[1]) if op == 1 else orc.intersect_sorted(lists)
+                eq(ho[int(hoff[qi]): int(hoff[qi + 1])], want, f"resident batch {bi} query {qi} op {op}")
+        _lib.check(lib.dgx_lane_set_resident_inputs(lane, 0))
+        lib.dgx_lane_destroy(lane)
