@@ -84,7 +84,6 @@ static u32 g_merge_stride = 6;         // DGX_MERGE_STRIDE: sample gaps per mult
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
 static size_t g_pre_throttle_smem = 0;  // DGX_PRE_THROTTLE: dynamic smem asked for by an ahead-of-time pre-pass (0 = unthrottled)
-static int g_plan_shared = 1;          // DGX_PLAN_SHARED=0: ahead-of-time pre-pass uses the two-search plan kernel too
 static u32 g_reserve_ctas = 0;         // DGX_RESERVE_CTAS: pipeline CTAs left out of the persistent grid
 static uint64_t g_pipe_min_values = 0;  // DGX_PIPE_MIN_VALUES: batches driving fewer values than this use filter_kernel
 static size_t g_pipe_min_k = 2;        // DGX_PIPE_MIN_K: batches whose widest query has fewer lists use filter_kernel
@@ -559,31 +558,24 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         g_stats.launches += 1;
     } else {
         // ---- persistent TMA pipeline: plan pre-pass + filter_pipe_kernel ----------------
-        // plan_base: [0, nq] first plan entry of every task (+ the total), [nq + 1 ..] boundary rows before it (used by
-        // the boundary-sharing pre-pass: a task has tiles + 1 boundaries)
         void* hp_raw;
-        rc = l->host.alloc((2 * nq + 2) * sizeof(u64), &hp_raw);
+        rc = l->host.alloc(nq * sizeof(u64), &hp_raw);
         if (rc) return rc;
         u64* h_pb = (u64*)hp_raw;
-        u64 npairs = 0, nextra = 0;
+        u64 npairs = 0;
         for (size_t q = 0; q < nq; ++q) {
             h_pb[q] = npairs;
-            h_pb[nq + 1 + q] = nextra;
             const u64 nt = (q + 1 < nq ? ht[q + 1].tile_base : ntiles) - ht[q].tile_base;
             npairs += nt * (u64)(ht[q].k - 1);
-            nextra += (u64)(ht[q].k - 1);
         }
-        h_pb[nq] = npairs;
-        h_pb[2 * nq + 1] = nextra;
-        const u64 nbound = npairs + nextra;
         void *d_pb, *d_plan, *d_tiles;
-        rc = ar->alloc((2 * nq + 2) * sizeof(u64), &d_pb);
+        rc = ar->alloc(nq * sizeof(u64), &d_pb);
         if (rc) return rc;
         rc = ar->alloc(ntiles * sizeof(PTileEntry), &d_tiles);
         if (rc) return rc;
         rc = ar->alloc((npairs + 1) * sizeof(PPlanEntry), &d_plan);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(d_pb, h_pb, (2 * nq + 2) * sizeof(u64), cudaMemcpyHostToDevice, pre));
+        CK(cudaMemcpyAsync(d_pb, h_pb, nq * sizeof(u64), cudaMemcpyHostToDevice, pre));
         // DGX_PRE_THROTTLE: dynamic shared memory an ahead-of-time pre-pass asks for (16 KB would limit it to one CTA on
         // an SM that holds two pipeline CTAs).  Measured: no effect (0.3559 vs 0.3565 ms) -- what the overlap costs the
         // pipeline is L2 / DRAM interference, not issue slots -- so the default is 0.
@@ -594,17 +586,10 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         l->launches += 1;
         g_stats.launches += 1;
         if (npairs) {
-            // ahead of time (latency hidden, traffic not): the boundary-sharing form; in line: the two-search form
-            const bool shared_plan = ahead && g_plan_shared;
-            const u64 nthreads = shared_plan ? nbound : npairs;
-            const u64 blocks = (nthreads + 255) / 256;
+            const u64 blocks = (npairs + 255) / 256;
             if (blocks > 0x7fffffffull) return fail(DGX_ERR_ARG, "batch too large");
-            if (shared_plan)
-                filter_plan_shared_kernel<<<(unsigned)blocks, 256, pre_smem, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, nbound,
-                                                                                    (PPlanEntry*)d_plan, (u32)tile_sz);
-            else
-                filter_plan_kernel<<<(unsigned)blocks, 256, pre_smem, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
-                                                                             (PPlanEntry*)d_plan, (u32)tile_sz);
+            filter_plan_kernel<<<(unsigned)blocks, 256, pre_smem, pre>>>(P.tasks, P.lists, (const u64*)d_pb, P.ntasks, npairs,
+                                                                         (PPlanEntry*)d_plan, (u32)tile_sz);
             CK(cudaGetLastError());
             l->launches += 1;
             g_stats.launches += 1;

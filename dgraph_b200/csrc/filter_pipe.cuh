@@ -102,18 +102,10 @@ struct PParams {
 };
 
 // ---- plan ---------------------------------------------------------------------------
-// Slice of filter list L_j a tile needs: r0 = first i with L[i] >= tile first, r1 = first i with L[i] > tile last.
-// Two formulations, same results:
-//  * filter_plan_kernel: one THREAD per (tile, list), both bounds as two interleaved binary searches -- the shortest
-//    dependent chain (the kernel is a latency chain of ~20 probes); used when the pre-pass is serialised in front of
-//    its pipeline kernel.
-//  * filter_plan_shared_kernel: one thread per (tile BOUNDARY, list).  r1 of tile t-1 and r0 of tile t differ only by
-//    the elements of L strictly between two CONSECUTIVE driving values (usually none): ONE binary search
-//    (lower_bound of tile t's first value) plus a walk back over the few elements above tile t-1's last value.
-//    ~45 % fewer probes but a longer chain (51 vs 43 us stand-alone); used when the pre-pass runs AHEAD, under the
-//    previous batch's pipeline kernel, where its latency is hidden and only its L2 / DRAM traffic costs.
-// (A binary search touches one new 32-byte sector per level only near its end, ~8 sectors, where a 32-ary warp search
-//  touches ~70: the plan must not cost a second pass over HBM.)
+// One THREAD per (tile, filter list): r0 = first i with L[i] >= tile first, r1 = first i
+// with L[i] > tile last, as two interleaved binary searches.  A binary search touches one
+// new 32-byte sector per level only near its end (~8 sectors), where the 32-ary warp
+// search of filter_kernel.cuh touches ~70: the plan must not cost a second pass over HBM.
 __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
                                                           const u64* __restrict__ plan_base, u32 ntasks, u64 npairs,
                                                           PPlanEntry* __restrict__ plan, u32 tile_sz) {
@@ -139,6 +131,30 @@ __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restric
         const FList Lj = lists[T.list_first + j];
         const u64* __restrict__ B = Lj.ptr;
         u64 l0 = 0, h0 = flist_len(Lj), l1 = 0, h1 = h0;
+#if DGX_PLAN_4ARY
+        // Both searches advance in lock step and 4-ary: three probes per search and level are in flight together, so
+        // the dependent chain is log4(n) memory latencies instead of log2(n) -- the kernel is a latency chain, not a
+        // bandwidth load (the extra probes touch ~1.5x the sectors of a binary search, a few MB per launch)
+        while (h0 - l0 > 3 || h1 - l1 > 3) {
+            const bool a = h0 - l0 > 3, c = h1 - l1 > 3;
+            const u64 q0 = (h0 - l0) >> 2, q1 = (h1 - l1) >> 2;
+            u64 a1 = 0, a2 = 0, a3 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if (a) { a1 = ld_probe(B + l0 + q0); a2 = ld_probe(B + l0 + 2 * q0); a3 = ld_probe(B + l0 + 3 * q0); }
+            if (c) { c1 = ld_probe(B + l1 + q1); c2 = ld_probe(B + l1 + 2 * q1); c3 = ld_probe(B + l1 + 3 * q1); }
+            if (a) {
+                if (a3 < tlo) l0 = l0 + 3 * q0 + 1;
+                else if (a2 < tlo) { h0 = l0 + 3 * q0; l0 = l0 + 2 * q0 + 1; }
+                else if (a1 < tlo) { h0 = l0 + 2 * q0; l0 = l0 + q0 + 1; }
+                else h0 = l0 + q0;
+            }
+            if (c) {
+                if (c3 <= thi) l1 = l1 + 3 * q1 + 1;
+                else if (c2 <= thi) { h1 = l1 + 3 * q1; l1 = l1 + 2 * q1 + 1; }
+                else if (c1 <= thi) { h1 = l1 + 2 * q1; l1 = l1 + q1 + 1; }
+                else h1 = l1 + q1;
+            }
+        }
+#endif
         while (l0 < h0 || l1 < h1) {
             const u64 m0 = l0 + ((h0 - l0) >> 1), m1 = l1 + ((h1 - l1) >> 1);
             const bool a = l0 < h0, c = l1 < h1;
@@ -150,64 +166,6 @@ __global__ void __launch_bounds__(256) filter_plan_kernel(const FTask* __restric
     }
     plan[p].r0 = r0;
     plan[p].r1 = r1;
-}
-
-constexpr int P_PLAN_WALK = 8;  // elements walked back before falling back to a second binary search
-// plan_base: [0, ntasks] first plan entry of every task (+ total); [ntasks + 1 + q] boundary rows before task q (k_q - 1
-// per earlier task): task q owns boundaries [plan_base[q] + rows[q], ...), (tiles_q + 1) x (k_q - 1) of them.
-__global__ void __launch_bounds__(256) filter_plan_shared_kernel(const FTask* __restrict__ tasks, const FList* __restrict__ lists,
-                                                                 const u64* __restrict__ plan_base, u32 ntasks, u64 nbound,
-                                                                 PPlanEntry* __restrict__ plan, u32 tile_sz) {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nbound) return;
-    u32 lo = 0, hi = ntasks;  // last task whose first boundary is <= p
-    while (hi - lo > 1) {
-        const u32 mid = (lo + hi) >> 1;
-        if (plan_base[mid] + plan_base[ntasks + 1 + mid] <= p) lo = mid; else hi = mid;
-    }
-    const FTask T = tasks[lo];
-    const u32 km1 = T.k - 1;
-    const u64 local = p - (plan_base[lo] + plan_base[ntasks + 1 + lo]);
-    const u64 bt = local / km1;                       // boundary index inside the task: 0 .. tiles
-    const u32 j = (u32)(local - bt * km1) + 1;
-    const u64 ntl = (plan_base[lo + 1] - plan_base[lo]) / km1;   // tiles of this task
-    const FList LA = lists[T.list_first];
-    const u64 lenA = flist_len(LA);
-    const FList Lj = lists[T.list_first + j];
-    const u64* __restrict__ B = Lj.ptr;
-    const u64 lenB = flist_len(Lj);
-    PPlanEntry* row = plan + plan_base[lo];           // entry (tile t, list j) = row[t * km1 + j - 1]
-    const u64 a0 = bt * (u64)tile_sz;                 // first driving value of tile bt
-    u64 r0 = 0;
-    const bool tile_real = bt < ntl && a0 < lenA;
-    if (tile_real) r0 = lower_bound_g(B, lenB, ld_probe(LA.ptr + a0));
-    if (bt < ntl) row[bt * km1 + (j - 1)].r0 = r0;    // tiles past the end of A keep the empty slice [0, 0)
-    if (bt > 0) {                                     // r1 of tile bt - 1
-        const u64 pa0 = (bt - 1) * (u64)tile_sz;
-        u64 r1 = 0;
-        if (pa0 < lenA) {
-            const u64 pend = pa0 + (u64)tile_sz < lenA ? pa0 + (u64)tile_sz : lenA;
-            const u64 last = ld_probe(LA.ptr + pend - 1);
-            u64 q = r0;
-            bool search = !tile_real;                 // last tile of the list: upper_bound(last value of A) from scratch
-            u64 sl = 0, sh = lenB;
-            if (tile_real) {
-                if (q < lenB && ld_probe(B + q) <= last) {
-                    search = true; sl = q;            // A repeats `last` across the boundary: the slice ends behind ITS copies
-                } else {
-                    int steps = 0;
-                    while (q > 0 && steps < P_PLAN_WALK && ld_probe(B + q - 1) > last) { --q; ++steps; }
-                    if (q > 0 && steps == P_PLAN_WALK && ld_probe(B + q - 1) > last) { search = true; sh = q; }
-                }
-            }
-            if (search) {
-                while (sl < sh) { const u64 m = sl + ((sh - sl) >> 1); if (ld_probe(B + m) <= last) sl = m + 1; else sh = m; }
-                q = sl;
-            }
-            r1 = q;
-        }
-        row[(bt - 1) * km1 + (j - 1)].r1 = r1;
-    }
 }
 
 // One thread per tile: which task it belongs to and where its driving values start.
