@@ -545,8 +545,8 @@ def test_filter_fast_path_stress(dgx, orc):
 # ---- resident-inputs lanes: the pre-pass of batch i+1 under the pipeline kernel of batch i -------------------------
 
 def test_resident_lane_batches(dgx, orc):
-    """dgx_lane_set_resident_inputs: batches queued back to back on one lane (their plan pre-pass -- the boundary-sharing
-    kernel -- runs ahead on a side stream, tables alternate between two workspaces).  Every batch is checked against the
+    """dgx_lane_set_resident_inputs: batches queued back to back on one lane (their plan pre-pass runs ahead on a side
+    stream, under the previous batch's pipeline kernel; tables alternate between two workspaces).  Every batch is checked against the
     oracle: wide queries, 2-list batches, Difference, duplicates repeated across tile boundaries, empty lists."""
     import torch
     from dgraph_b200 import _lib
