@@ -30,6 +30,7 @@
 #include "filter_pipe.cuh"
 #include "merge_kernel.cuh"
 #include "merge_multi.cuh"
+#include "merge_radix.cuh"
 #include "probe_kernel.cuh"
 #include "compressed_kernel.cuh"
 #include "encode_kernel.cuh"
@@ -80,6 +81,7 @@ static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's sli
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
+static int g_merge_radix = 1;          // DGX_MERGE=levels: tiles merged by pairwise levels (round-1 engine) instead of sorted
 static u32 g_merge_stride = 6;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values of a 4096 chunk)
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
@@ -248,7 +250,8 @@ extern "C" int dgx_init(int device) {
     g_num_sms = prop.multiProcessorCount;
     numa_probe(device);
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
-    if (const char* s = getenv("DGX_MERGE")) g_merge_multi = (strcmp(s, "tree") != 0);
+    CK(cudaFuncSetAttribute(mmerge2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MR_SMEM));
+    if (const char* s = getenv("DGX_MERGE")) { g_merge_multi = (strcmp(s, "tree") != 0); g_merge_radix = (strcmp(s, "levels") != 0); }
     if (const char* s = getenv("DGX_ZERO_COPY")) g_zero_copy = atoi(s) != 0;
     if (const char* s = getenv("DGX_MERGE_STRIDE")) { const int v = atoi(s); if (v >= 1 && v <= 7) g_merge_stride = (u32)v; }
     g_device = device;
@@ -800,7 +803,8 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     const size_t a_tin = a_bounds + (size_t)(nsamp + 2) * k * 8;
     const size_t a_tout = a_tin + (size_t)(nsamp + 2) * 8;
     const size_t a_tcnt = a_tout + (size_t)(nsamp + 3) * 8;
-    const size_t a_end = a_tcnt + (size_t)(nsamp + 2) * 4;
+    const size_t a_status = ((a_tcnt + (size_t)(nsamp + 2) * 4 + 255) & ~size_t(255));
+    const size_t a_end = a_status + (size_t)(nsamp + 3) * 8 + 256;  // look-back words + ticket (merge_radix.cuh)
     rc = l->ws.alloc(a_end, &d_raw);
     if (rc) return rc;
     void* d_scratch;
@@ -826,6 +830,10 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     P.out_cap = out_cap;
     P.out_len = (u64*)d_out_len;
     P.err = l->d_err;
+    const u32 max_tiles = nsamp / stride + 1;
+    P.nbs = max_tiles + 1;
+    P.status = (u64*)(d + a_status);
+    P.ticket = (u32*)(d + a_status + (size_t)(nsamp + 3) * 8);
     if (nsamp) {
         msample_kernel<<<(nsamp + 255) / 256, 256, 0, l->stream>>>(P);
         CK(cudaGetLastError());
@@ -845,8 +853,17 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     } else {
         CK(cudaMemsetAsync(d + a_nsplit, 0, 8, l->stream));
     }
-    const u32 max_tiles = nsamp / stride + 1;
     const uint64_t nb = (uint64_t)(max_tiles + 1) * k;
+    if (g_merge_radix) {
+        CK(cudaMemsetAsync(d + a_status, 0, (size_t)(nsamp + 3) * 8 + 256, l->stream));
+        mplan2_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
+        CK(cudaGetLastError());
+        mmerge2_kernel<<<max_tiles, MR_NT, MR_SMEM, l->stream>>>(P);
+        CK(cudaGetLastError());
+        l->launches += 2;
+        g_stats.launches += 2;
+        return DGX_OK;
+    }
     mplan_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
     CK(cudaGetLastError());
     mmerge_kernel<<<max_tiles, MM_NT, 2 * MM_CP * sizeof(u64), l->stream>>>(P);

@@ -56,6 +56,10 @@ struct MMParams {
     u64 out_cap;
     u64* out_len;
     int* err;
+    // merge_radix.cuh
+    u32 nbs;                // boundaries per run in the run-major bounds table (bounds[j * nbs + b])
+    u64* status;            // look-back words, one per tile, zeroed
+    u32* ticket;            // zeroed
 };
 
 // ---- samples ---------------------------------------------------------------------------
@@ -131,56 +135,20 @@ __device__ __forceinline__ void mm_merge_level(const u64* src, u64* dst, const i
 #undef MM_B
 }
 
-__global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
-    extern __shared__ __align__(16) u64 s_mm[];  // two ping-pong buffers of MM_C values
+// The levels engine for ONE tile: the slices [s_cur[r], s_end[r]) of the k runs s_ptr[r] are merged in rounds of at
+// most MM_C values (two ping-pong buffers of MM_CP values in s_mm), values equal to their predecessor are dropped and
+// the rest is appended to dst.  Called by all MM_NT threads of the CTA; returns the number of values written.
+__device__ __noinline__ u32 mm_levels_tile(u64* s_mm, const u64* const* s_ptr, u64* s_cur, const u64* s_end, int k,
+                                           u64* dst, bool have_last, u64 last) {
     u64* s_x = s_mm;
     u64* s_y = s_mm + MM_CP;
-    __shared__ u64 s_cur[MM_K], s_end[MM_K];
-    __shared__ const u64* s_ptr[MM_K];
     __shared__ int s_off[2][MM_K + 2];
-    __shared__ u64 s_red[8], s_tot[2], s_inc[2], s_mn[2], s_pad[2], s_tk[2];
+    __shared__ u64 s_tot[2], s_inc[2], s_mn[2], s_pad[2], s_tk[2];
     __shared__ int s_len[MM_K];
     __shared__ u64 s_bound;
     __shared__ u32 s_scan[MM_NT / 32 + 1];
-
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const u32 b = blockIdx.x;
-    const u32 ns = (u32)(*P.nsplit / P.stride);
-    if (b > ns) return;
-    const int k = (int)P.k;
-
-    // ---- the tile's slice of every run, its input offset and its predecessor value ------------
-    u64 my_c = 0;
-    u64 my_pred = 0;
-    bool my_has = false;
-    if (tid < k) {
-        const u64* p; u64 n;
-        mref_resolve(P.runs[tid], p, n);
-        const u64 c = P.bounds[(u64)b * k + tid], e = P.bounds[(u64)(b + 1) * k + tid];
-        s_ptr[tid] = p; s_cur[tid] = c; s_end[tid] = e;
-        my_c = c;
-        if (c > 0) { my_pred = ld_probe(p + c - 1); my_has = true; }
-    }
-    // block reductions over the first 64 threads (two warps): sum of starts, max predecessor
-    {
-        u64 sum = my_c, mx = my_has ? my_pred : 0;
-        u32 any = my_has ? 1u : 0u;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, d);
-            const u64 o = __shfl_xor_sync(0xffffffffu, mx, d);
-            mx = o > mx ? o : mx;
-            any |= __shfl_xor_sync(0xffffffffu, any, d);
-        }
-        if (lane == 0 && wid < 2) { s_red[wid] = sum; s_red[2 + wid] = mx; s_red[4 + wid] = any; }
-    }
-    __syncthreads();
-    const u64 inbase = s_red[0] + s_red[1];
-    bool have_last = (s_red[4] | s_red[5]) != 0;
-    u64 last = s_red[2] > s_red[3] ? s_red[2] : s_red[3];
-    u64* dst = P.scratch + inbase;
     u32 produced = 0;
-    __syncthreads();
 
     for (;;) {
         // ---- how much of every run enters this round -------------------------------------------
@@ -328,6 +296,52 @@ __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
         __syncthreads();
         if (fits) break;
     }
+    return produced;
+}
+
+__global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
+    extern __shared__ __align__(16) u64 s_mm[];  // two ping-pong buffers of MM_C values
+    __shared__ u64 s_cur[MM_K], s_end[MM_K];
+    __shared__ const u64* s_ptr[MM_K];
+    __shared__ u64 s_red[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 b = blockIdx.x;
+    const u32 ns = (u32)(*P.nsplit / P.stride);
+    if (b > ns) return;
+    const int k = (int)P.k;
+
+    // ---- the tile's slice of every run, its input offset and its predecessor value ------------
+    u64 my_c = 0;
+    u64 my_pred = 0;
+    bool my_has = false;
+    if (tid < k) {
+        const u64* p; u64 n;
+        mref_resolve(P.runs[tid], p, n);
+        const u64 c = P.bounds[(u64)b * k + tid], e = P.bounds[(u64)(b + 1) * k + tid];
+        s_ptr[tid] = p; s_cur[tid] = c; s_end[tid] = e;
+        my_c = c;
+        if (c > 0) { my_pred = ld_probe(p + c - 1); my_has = true; }
+    }
+    // block reductions over the first 64 threads (two warps): sum of starts, max predecessor
+    {
+        u64 sum = my_c, mx = my_has ? my_pred : 0;
+        u32 any = my_has ? 1u : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            const u64 o = __shfl_xor_sync(0xffffffffu, mx, d);
+            mx = o > mx ? o : mx;
+            any |= __shfl_xor_sync(0xffffffffu, any, d);
+        }
+        if (lane == 0 && wid < 2) { s_red[wid] = sum; s_red[2 + wid] = mx; s_red[4 + wid] = any; }
+    }
+    __syncthreads();
+    const u64 inbase = s_red[0] + s_red[1];
+    const bool have_last = (s_red[4] | s_red[5]) != 0;
+    const u64 last = s_red[2] > s_red[3] ? s_red[2] : s_red[3];
+    __syncthreads();
+    const u32 produced = mm_levels_tile(s_mm, s_ptr, s_cur, s_end, k, P.scratch + inbase, have_last, last);
     if (tid == 0) {
         P.tile_in[b] = inbase;
         P.tile_cnt[b] = produced;

@@ -1,0 +1,16 @@
+#!/bin/bash
+o=gpurun_out; mkdir -p $o
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "merge" -x > $o/m_tests.log 2>&1; tail -5 $o/m_tests.log
+timeout 200 python -m pytest tests/test_gpu_round2.py -m gpu -q -k "config5 or packed_ops or c5 or merge" -x > $o/m_tests2.log 2>&1; tail -3 $o/m_tests2.log
+timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -4
+DGX_MERGE=levels timeout 120 python tools/bench_merge.py 2>&1 | tail -1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $o/m_launches.csv python tools/bench_merge.py --reps 2 > $o/m_ncu.log 2>&1
+python - <<'PY'
+import csv,collections
+rows=list(csv.reader(l for l in open('gpurun_out/m_launches.csv') if l.startswith('"')))
+h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
+agg=collections.OrderedDict()
+for r in rows[1:]:
+    agg.setdefault(r[ki][:40],[]).append(float(r[vi].replace(',','')))
+for k,v in agg.items(): print(k,len(v),'avg us',round(sum(v)/len(v)/1e3,1))
+PY
