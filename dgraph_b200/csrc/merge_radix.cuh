@@ -21,6 +21,9 @@
 
 namespace dgx {
 
+#ifndef DGX_MR_MATCH
+#define DGX_MR_MATCH 1  // 1: hardware match.any; 0: one ballot per digit bit
+#endif
 constexpr int MR_NT = MM_NT;            // 512 threads
 constexpr int MR_NW = MR_NT / 32;       // 16 warps
 constexpr int MR_VT = 8;                // keys per thread and round
@@ -92,7 +95,17 @@ __device__ __forceinline__ u32* mr_sort(u32* a, u32* b, u32* cnt, u32* s_scan, i
                 const bool act = pos < n;
                 const u32 key = act ? src[pos] : 0u;
                 const u32 dig = act ? ((key >> shift) & mask) : 0xFFFFFFFFu;
+#if DGX_MR_MATCH
                 const unsigned peers = __match_any_sync(0xffffffffu, dig);
+#else
+                unsigned peers = __ballot_sync(0xffffffffu, act);  // lanes with the same digit: one ballot per digit bit
+#pragma unroll
+                for (int bit = 0; bit < MR_DB; ++bit) {
+                    const bool one = (dig >> bit) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, one);
+                    peers &= one ? m : ~m;
+                }
+#endif
                 const int leader = __ffs(peers) - 1;
                 u32 old = 0;
                 if (act && lane == leader) { old = myc[dig]; myc[dig] = old + __popc(peers); }
@@ -197,6 +210,10 @@ __global__ void __launch_bounds__(MR_NT, 3) mmerge2_kernel(const MMParams P) {
         const int passes = (bits + MR_DB - 1) / MR_DB;
         const int w = passes ? (bits + passes - 1) / passes : 0;
         direct = total <= (u64)MR_C;
+        // A value equal to a round's bound can have more copies waiting in runs that had loaded only part of them, so
+        // the last value written is remembered across rounds.
+        bool have_last = false;
+        u32 lastkey = 0;
         for (;;) {
             // ---- how much of every run enters this round ----------------------------------------------------
             u64 rem = 0;
@@ -278,12 +295,13 @@ __global__ void __launch_bounds__(MR_NT, 3) mmerge2_kernel(const MMParams P) {
                 if (pos < nsafe) {
                     const u32 v = Z[pos];
                     kv[j] = v;
-                    keep = pos == 0 || Z[pos - 1] != v;
+                    keep = pos == 0 ? (!have_last || v != lastkey) : (Z[pos - 1] != v);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if (keep) keepbits |= 1u << j;
                 if (lane == 0) s_cc[j * MR_NW + wid] = __popc(bal);
             }
+            if (nsafe > 0) { lastkey = Z[nsafe - 1]; have_last = true; }
             __syncthreads();
             if (wid == 0) {  // exclusive scan of the MR_VT * MR_NW = 128 chunk counts: four per lane
                 u32 c0 = s_cc[lane * 4], c1 = s_cc[lane * 4 + 1], c2 = s_cc[lane * 4 + 2], c3 = s_cc[lane * 4 + 3];

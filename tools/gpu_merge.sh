@@ -1,10 +1,9 @@
 #!/bin/bash
 o=gpurun_out; mkdir -p $o
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "merge" -x > $o/m_tests.log 2>&1; tail -5 $o/m_tests.log
-timeout 200 python -m pytest tests/test_gpu_round2.py -m gpu -q -k "config5 or packed_ops or c5 or merge" -x > $o/m_tests2.log 2>&1; tail -3 $o/m_tests2.log
-timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -4
-DGX_MERGE=levels timeout 120 python tools/bench_merge.py 2>&1 | tail -1
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $o/m_launches.csv python tools/bench_merge.py --reps 2 > $o/m_ncu.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "merge" -x > $o/m_tests.log 2>&1; tail -3 $o/m_tests.log
+timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -3
+echo ballot; DGX_LIB=$PWD/dgraph_b200/libdgx_mrballot.so timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -3
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"mmerge|mplan|msample|merge_kernel|mscan|mcompact" -c 40 --csv --log-file $o/m_launches.csv python tools/bench_merge.py --reps 1 > $o/m_ncu.log 2>&1
 python - <<'PY'
 import csv,collections
 rows=list(csv.reader(l for l in open('gpurun_out/m_launches.csv') if l.startswith('"')))
@@ -14,3 +13,4 @@ for r in rows[1:]:
     agg.setdefault(r[ki][:40],[]).append(float(r[vi].replace(',','')))
 for k,v in agg.items(): print(k,len(v),'avg us',round(sum(v)/len(v)/1e3,1))
 PY
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:mmerge2 -s 1 -c 1 -o $o/m_mmerge2 -f python tools/bench_merge.py --reps 1 > $o/m_ncu2.log 2>&1; tail -2 $o/m_ncu2.log
