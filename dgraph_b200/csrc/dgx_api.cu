@@ -30,7 +30,7 @@
 #include "filter_pipe.cuh"
 #include "merge_kernel.cuh"
 #include "merge_multi.cuh"
-#include "merge_radix.cuh"
+#include "merge_tile32.cuh"
 #include "probe_kernel.cuh"
 #include "compressed_kernel.cuh"
 #include "encode_kernel.cuh"
@@ -81,8 +81,9 @@ static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's sli
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
-static int g_merge_radix = 1;          // DGX_MERGE=levels: tiles merged by pairwise levels (round-1 engine) instead of sorted
-static u32 g_merge_stride = 6;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values of a 4096 chunk)
+static int g_merge_t32 = 1;            // DGX_MERGE=levels: the round-1 pipeline (64-bit levels engine, boundary-major bounds)
+static u32 g_merge_stride = 0;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values); 0 = 10 for the
+                                       // 32-bit engine (7680-slot rounds), 6 for DGX_MERGE=levels (4096-slot rounds)
 static int g_zero_copy = 0;            // DGX_ZERO_COPY=1: decode pinned packs in place over PCIe (measured slower than DMA: 35 vs 43 GB/s)
 static size_t g_merge_multi_min = size_t(1) << 18;  // totals below this stay on the tree (fewer launches)
 static size_t g_pre_throttle_smem = 0;  // DGX_PRE_THROTTLE: dynamic smem asked for by an ahead-of-time pre-pass (0 = unthrottled)
@@ -250,10 +251,10 @@ extern "C" int dgx_init(int device) {
     g_num_sms = prop.multiProcessorCount;
     numa_probe(device);
     if (const char* s = getenv("DGX_FILTER")) g_filter_pipe = (strcmp(s, "v4") != 0);
-    CK(cudaFuncSetAttribute(mmerge2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MR_SMEM));
-    if (const char* s = getenv("DGX_MERGE")) { g_merge_multi = (strcmp(s, "tree") != 0); g_merge_radix = (strcmp(s, "levels") != 0); }
+    CK(cudaFuncSetAttribute(mmerge3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
+    if (const char* s = getenv("DGX_MERGE")) { g_merge_multi = (strcmp(s, "tree") != 0); g_merge_t32 = (strcmp(s, "levels") != 0); }
     if (const char* s = getenv("DGX_ZERO_COPY")) g_zero_copy = atoi(s) != 0;
-    if (const char* s = getenv("DGX_MERGE_STRIDE")) { const int v = atoi(s); if (v >= 1 && v <= 7) g_merge_stride = (u32)v; }
+    if (const char* s = getenv("DGX_MERGE_STRIDE")) { const int v = atoi(s); if (v >= 1 && v <= 16) g_merge_stride = (u32)v; }
     g_device = device;
     return DGX_OK;
 }
@@ -785,7 +786,7 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     // Samples per run proportional to its length.  Every 4th distinct sample becomes a splitter, so a
     // tile is the sum of 4 sample gaps (~2K values on average, Gamma-distributed instead of
     // exponential) and rarely overflows the 4096-value shared-memory chunk.
-    const u32 stride = g_merge_stride;
+    const u32 stride = g_merge_stride ? (g_merge_t32 ? g_merge_stride : std::min<u32>(g_merge_stride, 7)) : (g_merge_t32 ? 10u : 6u);
     const uint64_t ntarget = std::min<uint64_t>(std::max<uint64_t>(total / 512, 1), uint64_t(1) << 24);
     std::vector<u32> soff(k + 1, 0);
     for (size_t j = 0; j < k; ++j) soff[j + 1] = soff[j] + (u32)((unsigned __int128)ub[j] * ntarget / total);
@@ -854,14 +855,17 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
         CK(cudaMemsetAsync(d + a_nsplit, 0, 8, l->stream));
     }
     const uint64_t nb = (uint64_t)(max_tiles + 1) * k;
-    if (g_merge_radix) {
-        CK(cudaMemsetAsync(d + a_status, 0, (size_t)(nsamp + 3) * 8 + 256, l->stream));
+    if (g_merge_t32) {
         mplan2_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
         CK(cudaGetLastError());
-        mmerge2_kernel<<<max_tiles, MR_NT, MR_SMEM, l->stream>>>(P);
+        mmerge3_kernel<<<max_tiles, T_NT, T_SMEM, l->stream>>>(P);
         CK(cudaGetLastError());
-        l->launches += 2;
-        g_stats.launches += 2;
+        mscan_kernel<<<1, 1024, 0, l->stream>>>(P);
+        CK(cudaGetLastError());
+        mcompact_kernel<<<max_tiles, 256, 0, l->stream>>>(P);
+        CK(cudaGetLastError());
+        l->launches += 4;
+        g_stats.launches += 4;
         return DGX_OK;
     }
     mplan_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
