@@ -62,6 +62,13 @@ __global__ void __launch_bounds__(256) mplan2_kernel(const MMParams P) {
     P.bounds[(u64)j * P.nbs + b] = pos;
 }
 
+__device__ __forceinline__ u32 t32_saddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 t32_lds(u32 a) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
 // One level of pairwise merges on u32 keys.  The 64 run slots of the round (run r = [off0[r], off0[r+1]), every slot a
 // multiple of T_VT long, padded with T_INF, unused slots empty) are merged as a complete binary tree: at level L the
 // groups of 2^L slots (2i, 2i+1) of src are merged into dst at the same positions, so a thread finds its pair from the
@@ -76,29 +83,30 @@ __device__ __forceinline__ void t32_merge_level(const u32* __restrict__ src, u32
     const int a0 = off0[first], a1 = off0[first + g], b1 = off0[first + 2 * g];
     const int na = a1 - a0, nb = b1 - a1;
     const int d = pos - a0;  // diagonal inside the pair
-    const u32* A = src + a0;
-    const u32* B = src + a1;
+    // 32-bit shared-memory addresses from here on: one register per cursor, ld.shared with no address arithmetic
+    const u32 sA = t32_saddr(src + a0), sB = t32_saddr(src + a1), sE = t32_saddr(src + b1);
     int l = d > nb ? d - nb : 0, h = d < na ? d : na;
+    const u32 sBd = sB + 4u * (u32)(d - 1);
     while (l < h) {
         const int m = (l + h) >> 1;
-        if (A[m] <= B[d - 1 - m]) l = m + 1; else h = m;
+        if (t32_lds(sA + 4u * (u32)m) <= t32_lds(sBd - 4u * (u32)m)) l = m + 1; else h = m;
     }
     // Serial steps without divergence: an exhausted side reads as T_INF, which also is the padding value, so "take A"
-    // is a plain av <= bv (when both are T_INF everything left is padding and either side will do); ia / ib are
-    // absolute positions in src, read only below their run's end.
-    int ia = a0 + l, ib = a1 + (d - l);
-    u32 av = ia < a1 ? src[ia] : T_INF, bv = ib < b1 ? src[ib] : T_INF;
+    // is a plain av <= bv (when both are T_INF everything left is padding and either side will do); the cursors are
+    // read only below their run's end (A ends where B starts).
+    u32 pa = sA + 4u * (u32)l, pb = sB + 4u * (u32)(d - l);
+    u32 av = pa < sB ? t32_lds(pa) : T_INF, bv = pb < sE ? t32_lds(pb) : T_INF;
     u32* o = dst + pos;
 #pragma unroll
     for (int s_ = 0; s_ < T_VT; ++s_) {
         const bool takeA = av <= bv;
         o[s_] = takeA ? av : bv;
-        ia += takeA ? 1 : 0;
-        ib += takeA ? 0 : 1;
-        const int idx = takeA ? ia : ib;
-        const int lim = takeA ? a1 : b1;
+        const u32 p = (takeA ? pa : pb) + 4u;
+        const u32 lim = takeA ? sB : sE;
         u32 nv = T_INF;
-        if (idx < lim) nv = src[idx];
+        if (p < lim) nv = t32_lds(p);
+        pa = takeA ? p : pa;
+        pb = takeA ? pb : p;
         av = takeA ? nv : av;
         bv = takeA ? bv : nv;
     }
@@ -115,6 +123,8 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
     __shared__ u64 s_tot[2], s_mn[2];
     __shared__ u32 s_inc[2], s_tk[2];
     __shared__ int s_len[MM_K];
+    __shared__ int s_coff[MM_K + 1];  // first 128-slot load piece of every run
+    __shared__ u32 s_cinc[2];
     __shared__ u64 s_bound;
     __shared__ u32 s_cc[256];
     __shared__ u32 s_rtot;
@@ -163,12 +173,14 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
         const u32 slot = (u32)(((take + T_VT - 1) / T_VT) * T_VT);
         // exclusive scan of the slots over the 64 run positions + min of the bounds + sum of takes
         if (wid < 2) {
-            u32 inc = slot, tsum = (u32)take;
+            const u32 pieces = (slot + 127u) >> 7;
+            u32 inc = slot, inc2 = pieces, tsum = (u32)take;
             u64 mn = bnd;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += v;
+                const u32 v2 = __shfl_up_sync(0xffffffffu, inc2, d);
+                if (lane >= d) { inc += v; inc2 += v2; }
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -176,15 +188,20 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
                 mn = o < mn ? o : mn;
                 tsum += __shfl_xor_sync(0xffffffffu, tsum, d);
             }
-            if (lane == 31) s_inc[wid] = inc;
+            if (lane == 31) { s_inc[wid] = inc; s_cinc[wid] = inc2; }
             if (lane == 0) { s_mn[wid] = mn; s_tk[wid] = tsum; }
+            s_coff[tid] = (int)(inc2 - pieces);
             // exclusive offset inside the warp; the second warp adds the first warp's total below
             s_len[tid] = (int)take;
             s_off[1][tid] = (int)(inc - slot);
         }
         __syncthreads();
-        if (tid < MM_K) s_off[0][tid] = s_off[1][tid] + (wid == 1 ? (int)s_inc[0] : 0);
+        if (tid < MM_K) {
+            s_off[0][tid] = s_off[1][tid] + (wid == 1 ? (int)s_inc[0] : 0);
+            if (wid == 1) s_coff[tid] += (int)s_cinc[0];
+        }
         if (tid == 0) {
+            s_coff[MM_K] = (int)(s_cinc[0] + s_cinc[1]);
             s_off[0][MM_K] = (int)(s_inc[0] + s_inc[1]);
             s_off[0][MM_K + 1] = s_off[0][MM_K];
             s_bound = s_mn[0] < s_mn[1] ? s_mn[0] : s_mn[1];
@@ -193,14 +210,28 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
         const int np = s_off[0][MM_K];                 // padded size of the chunk
         const int n = (int)(s_tk[0] + s_tk[1]);        // real values in the chunk
         const u64 bound = s_bound;
-        // ---- load the runs' contributions as offsets from lo, pad every slot (warp w: runs w, w+16, ...) -------
-        for (int r = wid; r < k; r += T_NT / 32) {
-            const int o = s_off[0][r], cnt = s_len[r], slot_n = s_off[0][r + 1] - o;
-            const u64* src = s_ptr[r] + s_cur[r];
-            for (int i = lane; i < slot_n; i += 32) s_x[o + i] = i < cnt ? (u32)(ld_stream(src + i) - lo) : T_INF;
+        // ---- load the runs' contributions as offsets from lo, pad every slot.  The runs are cut into pieces of 128
+        // slots and the pieces dealt to the warps round-robin: a run that holds a fifth of the tile does not make one
+        // warp the straggler of the barrier below.
+        {
+            const int nitems = s_coff[MM_K];
+            for (int it = wid; it < nitems; it += T_NT / 32) {
+                int l = 0, h = MM_K;  // last r with s_coff[r] <= it (runs without pieces share their successor's offset)
+                while (h - l > 1) {
+                    const int mid = (l + h) >> 1;
+                    if (s_coff[mid] <= it) l = mid; else h = mid;
+                }
+                const int r = l;
+                const int o = s_off[0][r], cnt = s_len[r], slot_n = s_off[0][r + 1] - o;
+                const u64* src = s_ptr[r] + s_cur[r];
+                const int base = (it - s_coff[r]) * 128 + lane;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = base + q * 32;
+                    if (i < slot_n) s_x[o + i] = i < cnt ? (u32)(ld_stream(src + i) - lo) : T_INF;
+                }
+            }
         }
-        __syncthreads();  // everyone has read s_off[0][r + 1] of the last real run before it changes
-        for (int r = k + tid; r <= MM_K; r += T_NT) s_off[0][r] = np;  // unused slots are empty runs
         __syncthreads();
         // ---- log2(64) levels of pairwise merges, ping-pong between s_x and s_y -------------------
         int r0 = 0;  // slot holding this thread's first position: last r with off0[r] <= pos

@@ -2,7 +2,7 @@
 o=gpurun_out; mkdir -p $o
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "merge" -x > $o/m_tests.log 2>&1; tail -3 $o/m_tests.log
 timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -3
-for s in 8 9 11 12; do echo stride $s; DGX_MERGE_STRIDE=$s timeout 120 python tools/bench_merge.py 2>&1 | tail -1; done
+for s in 9 11; do echo stride $s; DGX_MERGE_STRIDE=$s timeout 120 python tools/bench_merge.py 2>&1 | tail -1; done
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"mmerge|mplan|msample|merge_kernel|mscan|mcompact" -c 40 --csv --log-file $o/m_launches.csv python tools/bench_merge.py --reps 1 > $o/m_ncu.log 2>&1
 python - <<'PY'
 import csv,collections
