@@ -81,6 +81,7 @@ static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's sli
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
+static int g_merge_ahead = -1;         // DGX_MERGE_AHEAD: L2 prefetch distance in tiles (-1 = 3 x SM count, the resident CTAs; 0 = off)
 static int g_merge_t32 = 1;            // DGX_MERGE=levels: the round-1 pipeline (64-bit levels engine, boundary-major bounds)
 static u32 g_merge_stride = 0;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values); 0 = 10 for the
                                        // 32-bit engine (7680-slot rounds), 6 for DGX_MERGE=levels (4096-slot rounds)
@@ -254,6 +255,7 @@ extern "C" int dgx_init(int device) {
     CK(cudaFuncSetAttribute(mmerge3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
     if (const char* s = getenv("DGX_MERGE")) { g_merge_multi = (strcmp(s, "tree") != 0); g_merge_t32 = (strcmp(s, "levels") != 0); }
     if (const char* s = getenv("DGX_ZERO_COPY")) g_zero_copy = atoi(s) != 0;
+    if (const char* s = getenv("DGX_MERGE_AHEAD")) g_merge_ahead = atoi(s);
     if (const char* s = getenv("DGX_MERGE_STRIDE")) { const int v = atoi(s); if (v >= 1 && v <= 16) g_merge_stride = (u32)v; }
     g_device = device;
     return DGX_OK;
@@ -833,6 +835,7 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     P.err = l->d_err;
     const u32 max_tiles = nsamp / stride + 1;
     P.nbs = max_tiles + 1;
+    P.ahead = g_merge_ahead < 0 ? 3u * (u32)g_num_sms : (u32)g_merge_ahead;
     P.status = (u64*)(d + a_status);
     P.ticket = (u32*)(d + a_status + (size_t)(nsamp + 3) * 8);
     if (nsamp) {

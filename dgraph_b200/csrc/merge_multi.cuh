@@ -60,6 +60,7 @@ struct MMParams {
     u32 nbs;                // boundaries per run in the run-major bounds table (bounds[j * nbs + b])
     u64* status;            // look-back words, one per tile, zeroed
     u32* ticket;            // zeroed
+    u32 ahead;              // merge_tile32.cuh: prefetch the tile this many tiles on into L2 (0 = off)
 };
 
 // ---- samples ---------------------------------------------------------------------------

@@ -125,6 +125,7 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
     __shared__ int s_len[MM_K];
     __shared__ int s_coff[MM_K + 1];  // first 128-slot load piece of every run
     __shared__ u32 s_cinc[2];
+    __shared__ unsigned char s_prun[T_C / 128 + MM_K + 4];  // run of every load piece
     __shared__ u64 s_bound;
     __shared__ u32 s_cc[256];
     __shared__ u32 s_rtot;
@@ -213,14 +214,19 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
         // ---- load the runs' contributions as offsets from lo, pad every slot.  The runs are cut into pieces of 128
         // slots and the pieces dealt to the warps round-robin: a run that holds a fifth of the tile does not make one
         // warp the straggler of the barrier below.
+        const int nitems = s_coff[MM_K];  // <= T_C / 128 + MM_K
+        if (tid < nitems) {
+            int l = 0, h = MM_K;  // last r with s_coff[r] <= tid (runs without pieces share their successor's offset)
+            while (h - l > 1) {
+                const int mid = (l + h) >> 1;
+                if (s_coff[mid] <= tid) l = mid; else h = mid;
+            }
+            s_prun[tid] = (unsigned char)l;
+        }
+        __syncthreads();
         {
-            const int nitems = s_coff[MM_K];
             for (int it = wid; it < nitems; it += T_NT / 32) {
-                int l = 0, h = MM_K;  // last r with s_coff[r] <= it (runs without pieces share their successor's offset)
-                while (h - l > 1) {
-                    const int mid = (l + h) >> 1;
-                    if (s_coff[mid] <= it) l = mid; else h = mid;
-                }
+                const int l = s_prun[it];
                 const int r = l;
                 const int o = s_off[0][r], cnt = s_len[r], slot_n = s_off[0][r + 1] - o;
                 const u64* src = s_ptr[r] + s_cur[r];
@@ -372,6 +378,14 @@ __global__ void __launch_bounds__(T_NT, 3) mmerge3_kernel(const MMParams P) {
     const u64 total = s_r[0][1] + s_r[1][1];
     const u64 lo = s_r[0][2] < s_r[1][2] ? s_r[0][2] : s_r[1][2];
     const u64 hi = s_r[0][3] > s_r[1][3] ? s_r[0][3] : s_r[1][3];
+
+    // Pull the slices of the tile this SM slot will most likely run next (P.ahead tiles on) into L2 while this one is
+    // merged: its loads then pay an L2 hit instead of a DRAM round trip.
+    if (P.ahead && tid < k && b + P.ahead <= ns) {
+        const u64 c2 = P.bounds[(u64)tid * P.nbs + b + P.ahead], e2 = P.bounds[(u64)tid * P.nbs + b + P.ahead + 1];
+        const u64* q = s_ptr[tid];
+        for (u64 i = c2 & ~(u64)15; i < e2; i += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + i));
+    }
 
     // Equal values always fall into the same tile (every run is cut at lower_bound of the same splitter), so a tile
     // never has to look at its predecessor's last value.

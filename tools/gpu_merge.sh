@@ -2,7 +2,7 @@
 o=gpurun_out; mkdir -p $o
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "merge" -x > $o/m_tests.log 2>&1; tail -3 $o/m_tests.log
 timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -3
-for s in 9 11; do echo stride $s; DGX_MERGE_STRIDE=$s timeout 120 python tools/bench_merge.py 2>&1 | tail -1; done
+for a in 0 148 296 888; do echo ahead $a; DGX_MERGE_AHEAD=$a timeout 120 python tools/bench_merge.py 2>&1 | tail -1; done
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"mmerge|mplan|msample|merge_kernel|mscan|mcompact" -c 40 --csv --log-file $o/m_launches.csv python tools/bench_merge.py --reps 1 > $o/m_ncu.log 2>&1
 python - <<'PY'
 import csv,collections
@@ -13,4 +13,3 @@ for r in rows[1:]:
     agg.setdefault(r[ki][:40],[]).append(float(r[vi].replace(',','')))
 for k,v in agg.items(): print(k,len(v),'avg us',round(sum(v)/len(v)/1e3,1))
 PY
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:mmerge3 -s 1 -c 1 -o $o/m_mmerge3 -f python tools/bench_merge.py --reps 1 > $o/m_ncu2.log 2>&1; tail -2 $o/m_ncu2.log
