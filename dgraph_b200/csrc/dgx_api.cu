@@ -81,6 +81,7 @@ static u32 g_scap_override = 0;       // DGX_SCAP: force the filter kernel's sli
 constexpr u32 kScapMin = 8192, kScapMax = 65536;  // bytes
 static int g_filter_pipe = 1;          // DGX_FILTER=v4 selects the non-persistent kernel
 static int g_merge_multi = 1;          // DGX_MERGE=tree forces the pairwise merge tree
+static int g_merge_lag = -1;           // DGX_MERGE_LAG: a merge CTA moves the tile this many tiles back to the output (-1 = 6 x SM count; 0 = scan + compact kernels)
 static int g_merge_ahead = -1;         // DGX_MERGE_AHEAD: L2 prefetch distance in tiles (-1 = 3 x SM count, the resident CTAs; 0 = off)
 static int g_merge_t32 = 1;            // DGX_MERGE=levels: the round-1 pipeline (64-bit levels engine, boundary-major bounds)
 static u32 g_merge_stride = 0;         // DGX_MERGE_STRIDE: sample gaps per multiway-merge tile (tile ~ 512 x stride values); 0 = 10 for the
@@ -256,6 +257,7 @@ extern "C" int dgx_init(int device) {
     if (const char* s = getenv("DGX_MERGE")) { g_merge_multi = (strcmp(s, "tree") != 0); g_merge_t32 = (strcmp(s, "levels") != 0); }
     if (const char* s = getenv("DGX_ZERO_COPY")) g_zero_copy = atoi(s) != 0;
     if (const char* s = getenv("DGX_MERGE_AHEAD")) g_merge_ahead = atoi(s);
+    if (const char* s = getenv("DGX_MERGE_LAG")) g_merge_lag = atoi(s);
     if (const char* s = getenv("DGX_MERGE_STRIDE")) { const int v = atoi(s); if (v >= 1 && v <= 16) g_merge_stride = (u32)v; }
     g_device = device;
     return DGX_OK;
@@ -806,7 +808,8 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     const size_t a_tin = a_bounds + (size_t)(nsamp + 2) * k * 8;
     const size_t a_tout = a_tin + (size_t)(nsamp + 2) * 8;
     const size_t a_tcnt = a_tout + (size_t)(nsamp + 3) * 8;
-    const size_t a_status = ((a_tcnt + (size_t)(nsamp + 2) * 4 + 255) & ~size_t(255));
+    const size_t a_tlo = ((a_tcnt + (size_t)(nsamp + 2) * 4 + 255) & ~size_t(255));
+    const size_t a_status = a_tlo + (size_t)(nsamp + 2) * 8;
     const size_t a_end = a_status + (size_t)(nsamp + 3) * 8 + 256;  // look-back words + ticket (merge_radix.cuh)
     rc = l->ws.alloc(a_end, &d_raw);
     if (rc) return rc;
@@ -835,6 +838,8 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     P.err = l->d_err;
     const u32 max_tiles = nsamp / stride + 1;
     P.nbs = max_tiles + 1;
+    P.tile_lo = (u64*)(d + a_tlo);
+    P.lag = !g_merge_t32 ? 0u : g_merge_lag < 0 ? 6u * (u32)g_num_sms : (u32)g_merge_lag;
     P.ahead = g_merge_ahead < 0 ? 3u * (u32)g_num_sms : (u32)g_merge_ahead;
     P.status = (u64*)(d + a_status);
     P.ticket = (u32*)(d + a_status + (size_t)(nsamp + 3) * 8);
@@ -861,8 +866,16 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     if (g_merge_t32) {
         mplan2_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, l->stream>>>(P);
         CK(cudaGetLastError());
+        if (P.lag) CK(cudaMemsetAsync(d + a_status, 0, (size_t)(nsamp + 3) * 8 + 256, l->stream));
         mmerge3_kernel<<<max_tiles, T_NT, T_SMEM, l->stream>>>(P);
         CK(cudaGetLastError());
+        if (P.lag) {
+            mtail_kernel<<<std::min<u32>(P.lag, max_tiles), T_NT, 0, l->stream>>>(P);
+            CK(cudaGetLastError());
+            l->launches += 3;
+            g_stats.launches += 3;
+            return DGX_OK;
+        }
         mscan_kernel<<<1, 1024, 0, l->stream>>>(P);
         CK(cudaGetLastError());
         mcompact_kernel<<<max_tiles, 256, 0, l->stream>>>(P);

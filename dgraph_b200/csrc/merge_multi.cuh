@@ -61,6 +61,8 @@ struct MMParams {
     u64* status;            // look-back words, one per tile, zeroed
     u32* ticket;            // zeroed
     u32 ahead;              // merge_tile32.cuh: prefetch the tile this many tiles on into L2 (0 = off)
+    u32 lag;                // merge_tile32.cuh: a CTA moves the tile `lag` tiles before its own to the output (0 = scan + compact kernels)
+    u64* tile_lo;           // nsamp + 2: base of a tile's 32-bit scratch keys
 };
 
 // ---- samples ---------------------------------------------------------------------------
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(MM_NT, 3) mmerge_kernel(const MMParams P) {
     const u32 produced = mm_levels_tile(s_mm, s_ptr, s_cur, s_end, k, P.scratch + inbase, have_last, last);
     if (tid == 0) {
         P.tile_in[b] = inbase;
-        P.tile_cnt[b] = produced;
+        P.tile_cnt[b] = produced | 0x80000000u;  // scratch holds u64 values (mcompact_kernel)
     }
 }
 
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(1024) mscan_kernel(const MMParams P) {
     u64 base = 0;
     for (u32 start = 0; start < ntiles; start += 1024) {
         const u32 i = start + threadIdx.x;
-        const u32 v = i < ntiles ? P.tile_cnt[i] : 0u;
+        const u32 v = i < ntiles ? (P.tile_cnt[i] & 0x7fffffffu) : 0u;
         u32 total;
         const u32 off = block_exclusive_scan<1024>(v, s_warp, &total);
         if (i < ntiles) P.tile_out[i] = base + off;
@@ -376,11 +378,17 @@ __global__ void __launch_bounds__(256) mcompact_kernel(const MMParams P) {
     const u32 b = blockIdx.x;
     if (b >= ntiles) return;
     const u64 o = P.tile_out[b];
-    const u32 cnt = P.tile_cnt[b];
+    const u32 cnt = P.tile_cnt[b] & 0x7fffffffu;
     if (o + cnt > P.out_cap) return;  // error already flagged by mscan_kernel
-    const u64* src = P.scratch + P.tile_in[b];
     u64* dst = P.out + o;
-    for (u32 i = threadIdx.x; i < cnt; i += 256) st_stream(dst + i, ld_stream(src + i));
+    if (P.tile_cnt[b] & 0x80000000u) {  // u64 values
+        const u64* src = P.scratch + P.tile_in[b];
+        for (u32 i = threadIdx.x; i < cnt; i += 256) st_stream(dst + i, ld_stream(src + i));
+    } else {                            // 32-bit offsets from tile_lo (merge_tile32.cuh)
+        const u32* src = (const u32*)(P.scratch + P.tile_in[b]);
+        const u64 lo = P.tile_lo[b];
+        for (u32 i = threadIdx.x; i < cnt; i += 256) st_stream(dst + i, lo + __ldg(src + i));
+    }
 }
 
 }  // namespace dgx

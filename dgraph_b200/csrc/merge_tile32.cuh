@@ -62,6 +62,9 @@ __global__ void __launch_bounds__(256) mplan2_kernel(const MMParams P) {
     P.bounds[(u64)j * P.nbs + b] = pos;
 }
 
+__device__ __forceinline__ void t32_st_stream(u32* p, u32 v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ u32 t32_saddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u32 t32_lds(u32 a) {
     u32 v;
@@ -113,9 +116,10 @@ __device__ __forceinline__ void t32_merge_level(const u32* __restrict__ src, u32
 }
 
 // The 32-bit engine for one tile (same contract as mm_levels_tile): the slices [s_cur[r], s_end[r]) of the k runs are
-// merged in rounds of at most T_C slots as offsets from lo, repeats are dropped, lo + key is appended to dst.
+// merged in rounds of at most T_C slots as offsets from lo, repeats are dropped, the distinct KEYS (v - lo, 4 bytes each)
+// are appended to dst -- the compaction adds lo back, so the scratch pass moves half the bytes.
 // Every value of the tile must satisfy 0 <= v - lo < T_INF.  Called by all T_NT threads; returns the number written.
-__device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_cur, const u64* s_end, int k, u64* dst,
+__device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_cur, const u64* s_end, int k, u32* dst,
                                      u64 lo) {
     u32* s_x = s_k;
     u32* s_y = s_k + T_C;
@@ -307,12 +311,12 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
         }
         __syncthreads();
         {
-            u64* dstp = dst + produced;
+            u32* dstp = dst + produced;
 #pragma unroll
             for (int j = 0; j < T_VT; ++j) {
                 const bool keep = (keepbits >> j) & 1u;
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) st_stream(dstp + s_cc[j * (T_NT / 32) + wid] + __popc(bal & lt), lo + kv[j]);
+                if (keep) t32_st_stream(dstp + s_cc[j * (T_NT / 32) + wid] + __popc(bal & lt), kv[j]);
             }
             produced += s_rtot;
         }
@@ -336,19 +340,93 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
     return produced;
 }
 
+// ---- lagged compaction ------------------------------------------------------------------------------------------
+// A tile's place in the output is the sum of the counts of the tiles before it, known only when they are all done.
+// Waiting for it at the end of a tile retires the CTAs in order (measured: half the kernel's time spent waiting behind
+// the slowest tile); a scan kernel plus a compaction kernel cost a full extra pass on their own (220 us).  Instead a
+// tile writes its keys to scratch, publishes its count, and the CTA that starts P.lag tiles LATER -- when the tile and
+// its predecessors have long finished -- resolves the offset with a decoupled look-back that finds everything already
+// published, and moves the values to their final position before it begins its own tile: the copy is memory-bound and
+// runs under the other CTAs' merging.  mtail_kernel moves the last P.lag tiles.
+constexpr u32 kTileWide = 0x80000000u;  // tile_cnt flag: the tile's scratch holds u64 values, not u32 offsets from tile_lo
+
+__device__ __forceinline__ u64 t32_ldcg64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u32 t32_ldcg32(const u32* p) {
+    u32 v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One warp: output offset of tile t (its count must be, or is about to be, published in P.status[t]).
+// Returns the exclusive prefix; *agg gets the tile's count.
+__device__ __forceinline__ u64 t32_tile_offset(const MMParams& P, u32 t, int lane, u64* agg) {
+    u64 w = 0;
+    if (lane == 0) {
+        while (((w = ld_relaxed(P.status + t)) >> 62) == 0) __nanosleep(200);
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    *agg = w & kValMask;
+    const u64 base = lookback_exclusive<true, 100>(P.status, t, *agg, lane);
+    __threadfence();  // what the tile wrote before publishing its count is visible to the loads that follow
+    return base;
+}
+
+// All threads of the CTA: move tile t's values from scratch to out[base ..).
+template <int NT>
+__device__ __forceinline__ void t32_copy_tile(const MMParams& P, u32 t, u64 base, int tid) {
+    const u64 inb = t32_ldcg64(P.tile_in + t);
+    const u64 lo = t32_ldcg64(P.tile_lo + t);
+    const u32 c = t32_ldcg32(P.tile_cnt + t);
+    const u32 cnt = c & ~kTileWide;
+    if (c & kTileWide) {
+        const u64* src = P.scratch + inb;
+        for (u32 i = tid; i < cnt; i += NT)
+            if (base + i < P.out_cap) st_stream(P.out + base + i, t32_ldcg64(src + i));
+    } else {
+        const u32* src = (const u32*)(P.scratch + inb);
+        for (u32 i = tid; i < cnt; i += NT)
+            if (base + i < P.out_cap) st_stream(P.out + base + i, lo + t32_ldcg32(src + i));
+    }
+}
+
 __global__ void __launch_bounds__(T_NT, 3) mmerge3_kernel(const MMParams P) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ u64 s_cur[MM_K], s_end[MM_K];
     __shared__ const u64* s_ptr[MM_K];
     __shared__ u64 s_r[2][4];
+    __shared__ u64 s_cbase;
+    __shared__ u32 s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const u32 b = blockIdx.x;
+    // tiles are numbered in the order their CTAs start, so every tile before a running one has started (look-back)
+    if (tid == 0) s_tile = P.lag ? atomicAdd(P.ticket, 1u) : blockIdx.x;
+    __syncthreads();
+    const u32 b = s_tile;
     const u32 ns = (u32)(*P.nsplit / P.stride);
     if (b > ns) return;
     const int k = (int)P.k;
+    const bool docopy = P.lag != 0 && b >= P.lag;
+    if (docopy && wid == 2) {  // warps 0 and 1 read the tile's bounds meanwhile
+        u64 agg;
+        const u64 base = t32_tile_offset(P, b - P.lag, lane, &agg);
+        if (lane == 0) s_cbase = base;
+    }
 
     // ---- the tile's slice of every run; input offset, size, smallest and largest value ---------------------
+    // An interior tile holds the values in [S(b), S(b+1)) (S(b) = splitter of boundary b), which bounds its span without
+    // touching the runs; the first and the last tile read their runs' end values.
+    const bool interior = b >= 1 && b < ns;
+    u64 lo = 0, hi = 0;
+    bool exact = !interior;  // read the runs' end values (also when the splitters are too far apart for 32-bit keys
+    if (interior) {          // although the values between them may not be)
+        lo = P.splitters[(u64)b * P.stride - 1];
+        hi = P.splitters[(u64)(b + 1) * P.stride - 1] - 1;  // splitters are distinct and ascending: hi >= lo
+        exact = hi - lo >= (u64)T_INF;
+    }
     {
         u64 c = 0, len = 0, vmin = kU64Max, vmax = 0;
         if (tid < k) {
@@ -358,7 +436,7 @@ __global__ void __launch_bounds__(T_NT, 3) mmerge3_kernel(const MMParams P) {
             const u64 e = P.bounds[(u64)tid * P.nbs + b + 1];
             s_ptr[tid] = p; s_cur[tid] = c; s_end[tid] = e;
             len = e - c;
-            if (len) { vmin = ld_probe(p + c); vmax = ld_probe(p + e - 1); }
+            if (len && exact) { vmin = ld_probe(p + c); vmax = ld_probe(p + e - 1); }
         }
         if (wid < 2) {
 #pragma unroll
@@ -376,8 +454,10 @@ __global__ void __launch_bounds__(T_NT, 3) mmerge3_kernel(const MMParams P) {
     __syncthreads();
     const u64 inbase = s_r[0][0] + s_r[1][0];
     const u64 total = s_r[0][1] + s_r[1][1];
-    const u64 lo = s_r[0][2] < s_r[1][2] ? s_r[0][2] : s_r[1][2];
-    const u64 hi = s_r[0][3] > s_r[1][3] ? s_r[0][3] : s_r[1][3];
+    if (exact) {
+        lo = s_r[0][2] < s_r[1][2] ? s_r[0][2] : s_r[1][2];
+        hi = s_r[0][3] > s_r[1][3] ? s_r[0][3] : s_r[1][3];
+    }
 
     // Pull the slices of the tile this SM slot will most likely run next (P.ahead tiles on) into L2 while this one is
     // merged: its loads then pay an L2 hit instead of a DRAM round trip.
@@ -386,18 +466,48 @@ __global__ void __launch_bounds__(T_NT, 3) mmerge3_kernel(const MMParams P) {
         const u64* q = s_ptr[tid];
         for (u64 i = c2 & ~(u64)15; i < e2; i += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + i));
     }
+    if (docopy) t32_copy_tile<T_NT>(P, b - P.lag, s_cbase, tid);
 
     // Equal values always fall into the same tile (every run is cut at lower_bound of the same splitter), so a tile
     // never has to look at its predecessor's last value.
     u32 produced = 0;
+    const bool wide = hi - lo >= (u64)T_INF;
     if (total != 0) {
-        if (hi - lo < (u64)T_INF) produced = t32_tile((u32*)s_raw, s_ptr, s_cur, s_end, k, P.scratch + inbase, lo);
+        if (!wide) produced = t32_tile((u32*)s_raw, s_ptr, s_cur, s_end, k, (u32*)(P.scratch + inbase), lo);
         else produced = mm_levels_tile((u64*)s_raw, s_ptr, s_cur, s_end, k, P.scratch + inbase, false, 0);
     }
+    __syncthreads();  // every thread's scratch writes precede the fence below
     if (tid == 0) {
         P.tile_in[b] = inbase;
-        P.tile_cnt[b] = produced;
+        P.tile_lo[b] = lo;
+        P.tile_cnt[b] = produced | (wide ? kTileWide : 0u);
+        if (P.lag) {
+            __threadfence();
+            st_relaxed(P.status + b, kFlagAgg | (u64)produced);
+        }
     }
+}
+
+// The tiles no later CTA moves: tile ns - i for CTA i < min(lag, ns + 1).  The CTA of tile ns also reports the length.
+__global__ void __launch_bounds__(T_NT) mtail_kernel(const MMParams P) {
+    __shared__ u64 s_cbase;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 ns = (u32)(*P.nsplit / P.stride);
+    if (blockIdx.x > ns) return;
+    const u32 t = ns - blockIdx.x;
+    if (wid == 0) {
+        u64 agg;
+        const u64 base = t32_tile_offset(P, t, lane, &agg);
+        if (lane == 0) {
+            s_cbase = base;
+            if (t == ns) {
+                *P.out_len = base + agg;
+                if (base + agg > P.out_cap) atomicExch(P.err, 1);
+            }
+        }
+    }
+    __syncthreads();
+    t32_copy_tile<T_NT>(P, t, s_cbase, tid);
 }
 
 }  // namespace dgx
