@@ -340,14 +340,15 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
     return produced;
 }
 
-// ---- lagged compaction ------------------------------------------------------------------------------------------
+// ---- lagged compaction (optional: DGX_MERGE_LAG > 0; default is mscan_kernel + mcompact_kernel) --------------------
 // A tile's place in the output is the sum of the counts of the tiles before it, known only when they are all done.
 // Waiting for it at the end of a tile retires the CTAs in order (measured: half the kernel's time spent waiting behind
-// the slowest tile); a scan kernel plus a compaction kernel cost a full extra pass on their own (220 us).  Instead a
-// tile writes its keys to scratch, publishes its count, and the CTA that starts P.lag tiles LATER -- when the tile and
-// its predecessors have long finished -- resolves the offset with a decoupled look-back that finds everything already
-// published, and moves the values to their final position before it begins its own tile: the copy is memory-bound and
-// runs under the other CTAs' merging.  mtail_kernel moves the last P.lag tiles.
+// the slowest tile).  Here a tile writes its keys to scratch, publishes its count, and the CTA that starts P.lag tiles
+// LATER -- when the tile and its predecessors have long finished -- resolves the offset with a decoupled look-back that
+// finds everything already published, and moves the values to their final position before it begins its own tile;
+// mtail_kernel moves the last P.lag tiles.  Bit-exact, no waiting at lag >= 6 x SMs, but measured no faster than the
+// two extra kernels (C5: 1.69 vs 1.655 ms): the merge kernel is bound by its phases' latencies, not by issue slots, so
+// the copy phase costs what the compaction kernel costs.
 constexpr u32 kTileWide = 0x80000000u;  // tile_cnt flag: the tile's scratch holds u64 values, not u32 offsets from tile_lo
 
 __device__ __forceinline__ u64 t32_ldcg64(const u64* p) {

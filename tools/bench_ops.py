@@ -241,7 +241,7 @@ def run(L, S, quick):
     want = torch.unique(torch.cat(lists))
     ok = bool(nm == want.numel() and torch.equal(out[:nm], want))
     del want
-    rows.append(row("MergeSorted", f"C5: k=64 lists, lengths ~ 1/rank, total {tot} UIDs (thinnings of a {master.numel()} master); single-pass multiway merge (merge_multi.cuh)",
+    rows.append(row("MergeSorted", f"C5: k=64 lists, lengths ~ 1/rank, total {tot} UIDs (thinnings of a {master.numel()} master); single-pass multiway merge (merge_multi.cuh + merge_tile32.cuh)",
                     ms, tot, 8 * (tot + nm), ok, {"out": nm}))
     dlist = thin_gpu(master, 10_000_000 / S / master.numel(), gen)
     merged = out[:nm].clone()
