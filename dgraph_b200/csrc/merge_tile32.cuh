@@ -29,6 +29,10 @@ constexpr u32 T_INF = 0xFFFFFFFFu;          // padding key; real keys are < T_IN
 constexpr size_t T_SMEM_32 = (size_t)2 * T_C * sizeof(u32);
 constexpr size_t T_SMEM_64 = (size_t)2 * MM_CP * sizeof(u64);
 constexpr size_t T_SMEM = T_SMEM_32 > T_SMEM_64 ? T_SMEM_32 : T_SMEM_64;
+#ifndef DGX_T_PIECE
+#define DGX_T_PIECE 256
+#endif
+constexpr int T_PIECE = DGX_T_PIECE;         // slots per load piece (T_PIECE / 32 independent loads per lane)
 constexpr int T_NCH = T_VT * (T_NT / 32);   // 32-position chunks of a round (de-duplication scan)
 static_assert(T_NCH <= 256, "chunk scan handles 8 chunks per lane");
 static_assert(MM_K == 64, "six merge levels");
@@ -127,9 +131,9 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
     __shared__ u64 s_tot[2], s_mn[2];
     __shared__ u32 s_inc[2], s_tk[2];
     __shared__ int s_len[MM_K];
-    __shared__ int s_coff[MM_K + 1];  // first 128-slot load piece of every run
+    __shared__ int s_coff[MM_K + 1];  // first load piece of every run
     __shared__ u32 s_cinc[2];
-    __shared__ unsigned char s_prun[T_C / 128 + MM_K + 4];  // run of every load piece
+    __shared__ unsigned char s_prun[T_C / T_PIECE + MM_K + 4];  // run of every load piece
     __shared__ u64 s_bound;
     __shared__ u32 s_cc[256];
     __shared__ u32 s_rtot;
@@ -178,7 +182,7 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
         const u32 slot = (u32)(((take + T_VT - 1) / T_VT) * T_VT);
         // exclusive scan of the slots over the 64 run positions + min of the bounds + sum of takes
         if (wid < 2) {
-            const u32 pieces = (slot + 127u) >> 7;
+            const u32 pieces = (slot + (u32)T_PIECE - 1u) / (u32)T_PIECE;
             u32 inc = slot, inc2 = pieces, tsum = (u32)take;
             u64 mn = bnd;
 #pragma unroll
@@ -215,10 +219,10 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
         const int np = s_off[0][MM_K];                 // padded size of the chunk
         const int n = (int)(s_tk[0] + s_tk[1]);        // real values in the chunk
         const u64 bound = s_bound;
-        // ---- load the runs' contributions as offsets from lo, pad every slot.  The runs are cut into pieces of 128
+        // ---- load the runs' contributions as offsets from lo, pad every slot.  The runs are cut into pieces of T_PIECE
         // slots and the pieces dealt to the warps round-robin: a run that holds a fifth of the tile does not make one
         // warp the straggler of the barrier below.
-        const int nitems = s_coff[MM_K];  // <= T_C / 128 + MM_K
+        const int nitems = s_coff[MM_K];  // <= T_C / T_PIECE + MM_K
         if (tid < nitems) {
             int l = 0, h = MM_K;  // last r with s_coff[r] <= tid (runs without pieces share their successor's offset)
             while (h - l > 1) {
@@ -234,9 +238,9 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
                 const int r = l;
                 const int o = s_off[0][r], cnt = s_len[r], slot_n = s_off[0][r + 1] - o;
                 const u64* src = s_ptr[r] + s_cur[r];
-                const int base = (it - s_coff[r]) * 128 + lane;
+                const int base = (it - s_coff[r]) * T_PIECE + lane;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < T_PIECE / 32; ++q) {
                     const int i = base + q * 32;
                     if (i < slot_n) s_x[o + i] = i < cnt ? (u32)(ld_stream(src + i) - lo) : T_INF;
                 }
@@ -275,21 +279,22 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
             nsafe = l;
         }
         // ---- drop repeats; position order is (j, thread): chunk (j, warp) holds 32 consecutive positions -------
-        u32 kv[T_VT];
-        unsigned keepbits = 0;
+        unsigned keepbits = 0;  // bit j: position j * T_NT + tid is a first occurrence
 #pragma unroll
         for (int j = 0; j < T_VT; ++j) {
-            const int pos = j * T_NT + tid;
-            bool keep = false;
-            kv[j] = 0;
-            if (pos < nsafe) {
-                const u32 v = Z[pos];
-                kv[j] = v;
-                keep = pos == 0 ? (!have_last || v != lastkey) : (Z[pos - 1] != v);
+            if (j * T_NT < nsafe) {  // the same for the whole CTA
+                const int pos = j * T_NT + tid;
+                bool keep = false;
+                if (pos < nsafe) {
+                    const u32 v = Z[pos];
+                    keep = pos == 0 ? (!have_last || v != lastkey) : (Z[pos - 1] != v);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) keepbits |= 1u << j;
+                if (lane == 0) s_cc[j * (T_NT / 32) + wid] = __popc(bal);
+            } else if (lane == 0) {
+                s_cc[j * (T_NT / 32) + wid] = 0;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) keepbits |= 1u << j;
-            if (lane == 0) s_cc[j * (T_NT / 32) + wid] = __popc(bal);
         }
         if (nsafe > 0) { lastkey = Z[nsafe - 1]; have_last = true; }
         if (tid >= T_NCH && tid < 256) s_cc[tid] = 0;
@@ -314,9 +319,11 @@ __device__ __noinline__ u32 t32_tile(u32* s_k, const u64* const* s_ptr, u64* s_c
             u32* dstp = dst + produced;
 #pragma unroll
             for (int j = 0; j < T_VT; ++j) {
-                const bool keep = (keepbits >> j) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) t32_st_stream(dstp + s_cc[j * (T_NT / 32) + wid] + __popc(bal & lt), kv[j]);
+                if (j * T_NT < nsafe) {
+                    const bool keep = (keepbits >> j) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) t32_st_stream(dstp + s_cc[j * (T_NT / 32) + wid] + __popc(bal & lt), Z[j * T_NT + tid]);
+                }
             }
             produced += s_rtot;
         }

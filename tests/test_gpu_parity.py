@@ -381,10 +381,15 @@ def test_properties_at_scale(dgx):
     eq(m2.Uids, np.union1d(a, b), "union")
 
 
-def test_merge_multiway_forced(orc):
+@pytest.mark.parametrize("knobs", [{}, {"DGX_MERGE_STRIDE": "16"}, {"DGX_MERGE_LAG": "3"}, {"DGX_MERGE_LAG": "700"},
+                                   {"DGX_MERGE": "levels"}],
+                         ids=["default", "stride16", "lag3", "lag700", "levels"])
+def test_merge_multiway_forced(orc, knobs):
     """The multiway MergeSorted path with its size threshold removed (DGX_MERGE_MULTI_MIN=0), in a
     subprocess because libdgx reads its knobs once: known answers, random k, adversarial shapes that
-    force the block-wise rounds (identical lists, one dense cluster, long duplicate runs)."""
+    force the block-wise rounds (identical lists, one dense cluster, long duplicate runs).  Variants: tiles so large
+    that most need several rounds (stride 16), compaction inside the merge kernel at a lag smaller and larger than
+    the number of resident CTAs, and the round-1 pipeline (64-bit tile keys)."""
     import subprocess
     code = r'''
 import os, sys
@@ -424,7 +429,7 @@ edge = np.uint64(2**32 - 2) * np.arange(1, 20001, dtype=np.uint64)
 chk([edge, edge + np.uint64(1), edge[::2] + np.uint64(2**32 - 3)], "spans at the 32-bit boundary")
 print("MULTIWAY_OK")
 '''
-    env = dict(os.environ, DGX_MERGE_MULTI_MIN="0")
+    env = dict(os.environ, DGX_MERGE_MULTI_MIN="0", **knobs)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert "MULTIWAY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
