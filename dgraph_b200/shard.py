@@ -235,3 +235,147 @@ def run_sharded_pairs(dist, a_lists, b_lists, compute: Callable, device=None, pa
     mine = parts[rank]
     out, off = compute(mine, a_lists, b_lists)
     return gatherv_exact(dist, parts, out, off, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pattern 2: ONE huge operation over lists that start SHARDED BY LIST -- range-partition the uid space.
+#
+# The reference splits a posting list that outgrows one key by uid range (posting/list.go:580-646 iterator part
+# selection, :2260-2271 split policy); the same idea shards one huge MergeSorted over the GPUs: G-1 splitters cut the
+# uid space into G ranges, rank r merges range r of EVERY list, equal uids land on one rank (no cross-rank
+# duplicates), and the results concatenate in rank order.  When a rank holds only some of the lists, each list's
+# slice of range r has to travel to rank r first: one all-to-all, the single data-path collective of this package.
+# ---------------------------------------------------------------------------------------------------------------
+
+_SIGN = -(1 << 63)
+
+
+def _ukey(t):
+    """Order-preserving int64 key of a uint64 bit pattern held in an int64 tensor (uids above 2^63 sort last)."""
+    return t ^ _SIGN
+
+
+def range_splitters(dist, local_lists, oversample: int = 1024, device=None):
+    """world-1 uid splitters (int64 bit patterns of uint64 values, ascending, identical on every rank).
+
+    Every rank samples its lists at a common stride (one sample per `total / (world * oversample)` values, so a list
+    weighs in proportion to its length), the samples are all-gathered, sorted, and the i/world quantiles taken.
+    Two tiny collectives (totals, sample counts) + one all_gather of the samples."""
+    import torch
+
+    world = dist.get_world_size()
+    dev = device if device is not None else (local_lists[0].device if local_lists else torch.device("cpu"))
+    if world == 1:
+        return torch.zeros(0, dtype=torch.int64, device=dev)
+    tot_local = torch.tensor([sum(int(l.numel()) for l in local_lists)], dtype=torch.int64, device=dev)
+    tots = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(tots, tot_local)
+    total = int(tots.sum().item())
+    stride = max(total // (world * oversample), 1)
+    picks = [l[stride // 2:: stride] for l in local_lists if l.numel()]
+    mine = _ukey(torch.cat(picks)) if picks else torch.zeros(0, dtype=torch.int64, device=dev)
+    cnt = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
+    cnts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnts, cnt)
+    cnts_h = cnts.cpu().numpy()
+    cap = max(int(cnts_h.max()), 1)
+    send = torch.full((cap,), (1 << 63) - 1, dtype=torch.int64, device=dev)  # pads sort last as keys
+    send[: mine.numel()] = mine
+    allk = torch.empty(world * cap, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allk, send)
+    keys = torch.cat([allk[r * cap: r * cap + int(cnts_h[r])] for r in range(world)])
+    keys, _ = torch.sort(keys)
+    if keys.numel() == 0:
+        return torch.zeros(world - 1, dtype=torch.int64, device=dev)  # nothing anywhere: any splitters will do
+    idx = torch.tensor([(i * keys.numel()) // world for i in range(1, world)], dtype=torch.int64, device=dev)
+    return _ukey(keys[idx])
+
+
+def exchange_by_range(dist, local_lists, splitters, device=None):
+    """The all-to-all: rank r receives, from every rank, the slice [splitter[r-1], splitter[r]) of each of that rank's
+    lists.  Returns the received runs (sorted int64 tensors, grouped by source rank, then in the source's list
+    order; empty slices are dropped).  Slices are cut with lower_bound, so all copies of a uid go to ONE rank.
+
+    Collectives: all_to_all of the slice lengths (fixed size), one host read of the cuts and one of the received
+    lengths, all_to_all of the payload with the exact sizes (NCCL: ncclSend/ncclRecv inside one group)."""
+    import torch
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    dev = device if device is not None else (local_lists[0].device if local_lists else splitters.device)
+    if world == 1:
+        return [l for l in local_lists if l.numel()]
+    nl = torch.tensor([len(local_lists)], dtype=torch.int64, device=dev)
+    nls = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(nls, nl)
+    lmax = max(int(nls.max().item()), 1)
+    skey = _ukey(splitters)
+    # cut[l, d] .. cut[l, d + 1] = slice of local list l that belongs to rank d
+    pieces = [[] for _ in range(world)]
+    lens_to_h = np.zeros((world, lmax), dtype=np.int64)
+    if local_lists:
+        cuts = torch.stack([torch.searchsorted(_ukey(l), skey, right=False) if l.numel()
+                            else torch.zeros(world - 1, dtype=torch.int64, device=dev) for l in local_lists])
+        cuts_h = cuts.cpu().numpy()                                       # one host read for all the lists
+        for li, l in enumerate(local_lists):
+            cut_h = [0] + [int(c) for c in cuts_h[li]] + [int(l.numel())]
+            for d in range(world):
+                n = cut_h[d + 1] - cut_h[d]
+                lens_to_h[d, li] = n
+                if n:
+                    pieces[d].append(l[cut_h[d]: cut_h[d + 1]])
+    lens_to = torch.from_numpy(lens_to_h).to(dev)
+    lens_from = torch.empty_like(lens_to)
+    dist.all_to_all_single(lens_from.view(-1), lens_to.view(-1))          # row s of lens_from: rank s's slices for me
+    lens_from_h = lens_from.cpu().numpy()                                    # the one host synchronisation
+    in_split = [int(sum(int(p.numel()) for p in pieces[d])) for d in range(world)]
+    out_split = [int(lens_from_h[s].sum()) for s in range(world)]
+    send = torch.cat([p for d in range(world) for p in pieces[d]]) if sum(in_split) else torch.zeros(0, dtype=torch.int64, device=dev)
+    recv = torch.empty(sum(out_split), dtype=torch.int64, device=dev)
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
+    else:  # gloo: grouped point-to-point transfers of the exact sizes
+        ops, so, ro = [], 0, 0
+        for r in range(world):
+            if r == rank:
+                recv[ro: ro + out_split[r]].copy_(send[so: so + in_split[r]])
+            else:
+                if in_split[r]:
+                    ops.append(dist.P2POp(dist.isend, send[so: so + in_split[r]], r))
+                if out_split[r]:
+                    ops.append(dist.P2POp(dist.irecv, recv[ro: ro + out_split[r]], r))
+            so += in_split[r]
+            ro += out_split[r]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+    runs, o = [], 0
+    for s in range(world):
+        for li in range(lmax):
+            n = int(lens_from_h[s, li])
+            if n:
+                runs.append(recv[o: o + n])
+            o += n
+    return runs
+
+
+def run_range_merge(dist, local_lists, merge: Callable, gather: bool = True, oversample: int = 1024, device=None):
+    """MergeSorted over lists sharded BY LIST across the process group (every rank passes the lists it holds).
+
+    merge(runs) -> sorted, de-duplicated int64 tensor of the runs this rank received (on a GPU box: one
+    dgx_dev_merge_sorted launch).  gather=True returns the whole result on every rank (rank-ordered all-gatherv, so
+    ascending); gather=False returns this rank's uid range only (what a following range-partitioned operation wants).
+    Also returns the splitters, so a second operand can be cut the same way (exchange_by_range)."""
+    import torch
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    spl = range_splitters(dist, local_lists, oversample=oversample, device=device)
+    runs = exchange_by_range(dist, local_lists, spl, device=device)
+    mine = merge(runs)
+    if not gather or world == 1:
+        return mine, spl
+    parts = [np.array([r]) for r in range(world)]
+    off = torch.tensor([0, int(mine.numel())], dtype=torch.int64, device=mine.device)
+    out, _ = gatherv_exact(dist, parts, mine, off, device=device)
+    return out, spl

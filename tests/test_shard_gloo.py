@@ -135,3 +135,74 @@ def test_gatherv_contiguous_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker_contig, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_range(rank, world, port, ret):
+    """Range-partitioned MergeSorted over lists sharded by list (SURVEY 8e pattern 2): splitters, all-to-all of the
+    slices, local merge (the oracle stands in for the kernel here; tests/test_gpu_multirank.py runs it with
+    dgx_dev_merge_sorted underneath), rank-ordered all-gatherv.  Then the second operand cut by the same splitters."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import gen
+        from dgraph_b200.shard import exchange_by_range, run_range_merge
+        from oracle import pyoracle as orc
+
+        def as_t(a):
+            return torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy())
+
+        def merge(runs):
+            if not runs:
+                return torch.zeros(0, dtype=torch.int64)
+            return as_t(orc.merge_sorted([r.numpy().view(np.uint64) for r in runs]))
+
+        rng = np.random.default_rng(11)  # same inputs on every rank; rank r HOLDS lists r, r + world, ...
+        master = gen.zipf_gaps(rng, 60000)
+        cases = {
+            "skewed": [gen.thin(rng, master, 1.0 / (i + 1)) for i in range(11)],
+            "with empties and duplicates": [np.zeros(0, np.uint64), np.sort(rng.integers(0, 500, 4000).astype(np.uint64)),
+                                            np.zeros(0, np.uint64), np.arange(100, 900, dtype=np.uint64), np.full(300, 7, np.uint64)],
+            "fewer lists than ranks": [master[::3]],
+            "nothing at all": [],
+            "above 2^63": [np.sort(rng.integers(0, 2**64 - 1, 5000, dtype=np.uint64)) for _ in range(5)]
+                          + [np.array([0, 2**63 - 1, 2**63, 2**64 - 1], dtype=np.uint64)],
+        }
+        ok = True
+        for name, lists in cases.items():
+            mine = [as_t(l) for l in lists[rank::world]]
+            want = orc.merge_sorted(lists) if lists else np.zeros(0, np.uint64)
+            out, spl = run_range_merge(dist, mine, merge, oversample=64)
+            ok = ok and np.array_equal(out.numpy().view(np.uint64), want)
+            part, _ = run_range_merge(dist, mine, merge, gather=False, oversample=64)
+            parts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(parts, torch.tensor([part.numel()]))
+            ok = ok and sum(int(p.item()) for p in parts) == want.size          # ranges are disjoint: no cross-rank repeats
+            # a second operand held by rank 0 only, cut by the same splitters: every rank gets its range of it
+            d = gen.thin(rng, master, 0.3)
+            got = exchange_by_range(dist, [as_t(d)] if rank == 0 else [], spl)
+            sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([sum(int(g.numel()) for g in got)]))
+            ok = ok and sum(int(s.item()) for s in sizes) == d.size
+            if got and part.numel():
+                lo, hi = int(part.numpy().view(np.uint64).min()), int(part.numpy().view(np.uint64).max())
+                g = torch.cat(got).numpy().view(np.uint64)
+                skey = spl.numpy().view(np.uint64)
+                if rank > 0:
+                    ok = ok and bool((g >= skey[rank - 1]).all())
+                if rank < world - 1:
+                    ok = ok and bool((g < skey[rank]).all())
+                del lo, hi
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_range_merge_gloo(world):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_range, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: True for r in range(world)}

@@ -10,6 +10,9 @@
       cross-rank duplicates), every rank merges its range of every list and subtracts the same
       range of the second operand, results are concatenated in rank order (all-gatherv).  Inputs
       are replicated on every rank here (same seed), so the all-to-all exchange is skipped.
+  C5-sharded  the same operation with the lists sharded BY LIST (rank r holds lists r, r + N, ...): splitters from a
+      strided sample of every rank's lists, one all-to-all of the slices (shard.exchange_by_range), local merge and
+      difference, all-gatherv -- everything inside the timed region.
 
     python -m torch.distributed.run --nproc-per-node N tools/bench_multi.py [--pairs 10000] [--merge-total 1e8]
 
@@ -202,6 +205,53 @@ def main():
                           "out_uids": nres, "check": ok,
                           "note": "range-partitioned MergeSorted + Difference, inputs replicated, rank-ordered all-gatherv inside the timed region"}),
               flush=True)
+    # ---------------- C5, lists sharded BY LIST ---------------------------------------------------------
+    # rank r holds lists r, r + world, ... (and rank 0 the second operand): splitters from a strided sample, ONE
+    # all-to-all of the slices (shard.exchange_by_range), then the same local merge + difference + all-gatherv.
+    if world > 1:
+        mine = lists[rank::world]
+        held_d = [dlist] if rank == 0 else []
+        res6 = {}
+
+        def merge_runs(runs):
+            n = len(runs)
+            tot = sum(int(r.numel()) for r in runs)
+            out = torch.empty(tot + 8, dtype=torch.int64, device=dev)
+            ln = torch.zeros(1, dtype=torch.int64, device=dev)
+            if n:
+                _lib.check(lib.dgx_dev_merge_sorted(lane, (C.c_void_p * n)(*[r.data_ptr() for r in runs]),
+                                                    (C.c_size_t * n)(*[int(r.numel()) for r in runs]), n,
+                                                    C.c_void_p(out.data_ptr()), out.numel(), C.c_void_p(ln.data_ptr())))
+            torch.cuda.current_stream().synchronize()
+            return out[: int(ln.item())]
+
+        def c6_step(gather=True, exchange_only=False):
+            part, spl = shard.run_range_merge(dist, mine, (lambda runs: runs) if exchange_only else merge_runs,
+                                              gather=False, device=dev)
+            if exchange_only:
+                return
+            dr = shard.exchange_by_range(dist, held_d, spl, device=dev)
+            dpart = dr[0] if dr else torch.zeros(0, dtype=torch.int64, device=dev)
+            out = torch.empty(int(part.numel()) + 8, dtype=torch.int64, device=dev)
+            off = torch.zeros(2, dtype=torch.int64, device=dev)
+            if part.numel():
+                p2 = (C.c_void_p * 2)(part.data_ptr(), dpart.data_ptr())
+                l2 = (C.c_size_t * 2)(int(part.numel()), int(dpart.numel()))
+                _lib.check(lib.dgx_dev_filter_batch(lane, _lib.OP_DIFFERENCE, p2, l2, (C.c_size_t * 2)(0, 2), 1,
+                                                    C.c_void_p(out.data_ptr()), int(part.numel()), C.c_void_p(off.data_ptr())))
+            res6["g"] = shard.gatherv_exact(dist, [[0]] * world, out, off, device=dev) if gather else (out, off)
+
+        ms_x = timed(lambda: c6_step(exchange_only=True))
+        ms6 = timed(c6_step)
+        gout, goff = res6["g"]
+        if rank == 0:
+            nres = int(goff[-1].item())
+            ok = bool(nres == want.numel() and torch.equal(gout[:nres], want))
+            print(json.dumps({"config": "C5-sharded", "n_gpus": world, "k": 64, "total_uids": tin, "ms": ms6,
+                              "ms_splitters_and_exchange": ms_x, "uids_per_s": (tin + dlist.numel()) / (ms6 * 1e-3),
+                              "out_uids": nres, "check": ok,
+                              "note": "lists sharded by list: splitters + all-to-all of the slices + local merge + difference + rank-ordered all-gatherv, all inside the timed region"}),
+                  flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
