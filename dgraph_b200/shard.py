@@ -1,4 +1,5 @@
-"""Multi-GPU sharding of batches of independent set operations (pattern 1).
+"""Multi-GPU sharding: batches of independent set operations (pattern 1, below) and one huge
+MergeSorted range-partitioned over lists that are sharded by list (pattern 2, at the end of the file).
 
 The reference fans a batch of independent posting-list intersections over
 goroutines (x.DivideAndRule, worker/task.go:816-987); here the same batch is
