@@ -664,6 +664,8 @@ static int merge_tree_impl(dgx_lane* l, std::vector<MRef> cur, std::vector<uint6
                            uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
 static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const std::vector<uint64_t>& ub, uint64_t total,
                             uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
+static int merge_runs_impl(dgx_lane* l, const std::vector<MRef>& cur, const std::vector<uint64_t>& ub, uint64_t total,
+                           uint64_t* d_out, size_t out_cap, uint64_t* d_out_len);
 
 static int merge_sorted_impl(dgx_lane* l, const ListDesc* lists, size_t k, uint64_t* d_out, size_t out_cap,
                              uint64_t* d_out_len) {
@@ -683,9 +685,47 @@ static int merge_sorted_impl(dgx_lane* l, const ListDesc* lists, size_t k, uint6
         return DGX_OK;
     }
     if (out_cap < total) return fail(DGX_ERR_CAP, "MergeSorted needs out_cap >= sum(lens) = %llu", (unsigned long long)total);
-    if (g_merge_multi && cur.size() >= 3 && cur.size() <= (size_t)MM_K && total >= g_merge_multi_min)
+    return merge_runs_impl(l, cur, ub, total, d_out, out_cap, d_out_len);
+}
+
+// Dispatch over the number of runs: the single-pass multiway merge for 3..64 large runs, groups of <= 64 runs merged
+// multiway into intermediate runs (whose lengths stay on the device: MRef::off) and merged again for more -- two passes
+// over HBM up to 4096 runs instead of ceil(log2 k) -- and the pairwise tree for everything small.
+static int merge_runs_impl(dgx_lane* l, const std::vector<MRef>& cur, const std::vector<uint64_t>& ub, uint64_t total,
+                           uint64_t* d_out, size_t out_cap, uint64_t* d_out_len) {
+    const size_t k = cur.size();
+    if (g_merge_multi && k >= 3 && k <= (size_t)MM_K && total >= g_merge_multi_min)
         return merge_multi_impl(l, cur, ub, total, d_out, out_cap, d_out_len);
-    return merge_tree_impl(l, cur, ub, total, d_out, out_cap, d_out_len);
+    const size_t ngroups = (k + MM_K - 1) / MM_K;
+    // a multiway call is a dozen launches: grouping pays only when every group is a few times the multiway minimum
+    if (!g_merge_multi || k <= (size_t)MM_K || total / ngroups < 4 * g_merge_multi_min)
+        return merge_tree_impl(l, cur, ub, total, d_out, out_cap, d_out_len);
+    const size_t gsz = (k + ngroups - 1) / ngroups;
+    void *d_tmp, *d_pairs;
+    int rc = l->ws.alloc(total * sizeof(u64), &d_tmp);
+    if (rc) return rc;
+    rc = l->ws.alloc(2 * ngroups * sizeof(u64), &d_pairs);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_pairs, 0, 2 * ngroups * sizeof(u64), l->stream));
+    std::vector<MRef> next;
+    std::vector<uint64_t> nub;
+    uint64_t goff = 0;
+    for (size_t g = 0; g < ngroups; ++g) {
+        const size_t b = g * gsz, e = std::min(k, b + gsz);
+        if (b >= e) break;
+        std::vector<MRef> part(cur.begin() + b, cur.begin() + e);
+        std::vector<uint64_t> pub(ub.begin() + b, ub.begin() + e);
+        uint64_t tot = 0;
+        for (uint64_t v : pub) tot += v;
+        u64* dst = (u64*)d_tmp + goff;
+        u64* pair = (u64*)d_pairs + 2 * g;  // {0, length of the group's merged run}
+        rc = merge_runs_impl(l, part, pub, tot, (uint64_t*)dst, tot, (uint64_t*)(pair + 1));
+        if (rc) return rc;
+        next.push_back(MRef{dst, pair, (u64)tot});
+        nub.push_back(tot);
+        goff += tot;
+    }
+    return merge_runs_impl(l, next, nub, total, d_out, out_cap, d_out_len);
 }
 
 // Pairwise merge tree: ceil(log2 k) passes of merge_kernel.

@@ -410,6 +410,12 @@ for lists, want in MERGE_CASES:
 rng = np.random.default_rng(77)
 for k in (3, 4, 5, 17, 33, 63, 64):
     chk([np.sort(rng.integers(0, 50000, int(rng.integers(0, 3000)), dtype=np.uint64)) for _ in range(k)], f"small k={k}")
+# more than 64 lists: groups of <= 64 merged multiway into intermediate runs (device-side lengths), then merged again
+for k in (65, 130, 257):
+    chk([np.sort(rng.integers(0, 200000, int(rng.integers(0, 4000)), dtype=np.uint64)) for _ in range(k)], f"grouped k={k}")
+wide = gen.zipf_gaps(rng, 1500000)
+chk([gen.thin(rng, wide, float(rng.uniform(0.002, 0.03))) for _ in range(200)], "grouped k=200, 3e6 values")
+chk([np.zeros(0, np.uint64)] * 70 + [wide[::5], wide[1::7]] + [np.zeros(0, np.uint64)] * 70, "mostly empty, k=142")
 master = gen.zipf_gaps(rng, 400000)
 chk([master] * 64, "64 identical lists")
 chk([master[::3], master[1::3], master[2::3]] * 8, "interleaved x8")

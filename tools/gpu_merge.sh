@@ -1,16 +1,43 @@
 #!/bin/bash
 o=gpurun_out; mkdir -p $o
 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "merge" -x > $o/m_tests.log 2>&1; tail -3 $o/m_tests.log
-timeout 120 python tools/bench_merge.py --dense 2>&1 | tail -3
-echo p128; DGX_LIB=$PWD/dgraph_b200/libdgx_p128.so timeout 120 python tools/bench_merge.py 2>&1 | tail -1
-for s in 9 11; do echo stride $s; DGX_MERGE_STRIDE=$s timeout 120 python tools/bench_merge.py 2>&1 | tail -1; done
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"mmerge|mplan|msample|merge_kernel|mscan|mcompact|mtail" -c 40 --csv --log-file $o/m_launches.csv python tools/bench_merge.py --reps 1 > $o/m_ncu.log 2>&1
-python - <<'PY'
-import csv,collections
-rows=list(csv.reader(l for l in open('gpurun_out/m_launches.csv') if l.startswith('"')))
-h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
-agg=collections.OrderedDict()
-for r in rows[1:]:
-    agg.setdefault(r[ki][:40],[]).append(float(r[vi].replace(',','')))
-for k,v in agg.items(): print(k,len(v),'avg us',round(sum(v)/len(v)/1e3,1))
+timeout 200 python - <<'PY'
+import ctypes as C, json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.getcwd())
+from tools.bench_ops import Lane, zipf_gaps_gpu, thin_gpu, timeit, DEV
+gen = torch.Generator(device=DEV); gen.manual_seed(9)
+L = Lane()
+master = zipf_gaps_gpu(200_000_000, gen)
+for k in (64, 256, 1024):
+    lists = [thin_gpu(master, 0.5 / k, gen) for _ in range(k)]
+    tot = sum(t.numel() for t in lists)
+    out = torch.empty(tot + 8, dtype=torch.int64, device=DEV); out_len = torch.zeros(1, dtype=torch.int64, device=DEV)
+    res = {}
+    for mode in ("grouped", "tree"):
+        if mode == "tree":
+            os.environ["DGX_MERGE"] = "tree"   # read once at dgx_init: needs a fresh process, so only report grouped here
+            break
+        ms, _ = timeit(lambda: L.merge(lists, out, out_len), warm=2, reps=5)
+        L.sync(); nm = int(out_len.item())
+        ok = bool(torch.equal(out[:nm], torch.unique(torch.cat(lists))))
+        res[mode] = (round(ms, 3), ok)
+    print(json.dumps({"k": k, "total": tot, "ms": res["grouped"][0], "check": res["grouped"][1]}), flush=True)
+    del lists, out
+PY
+DGX_MERGE=tree timeout 200 python - <<'PY'
+import json, os, sys
+import torch
+sys.path.insert(0, os.getcwd())
+from tools.bench_ops import Lane, zipf_gaps_gpu, thin_gpu, timeit, DEV
+gen = torch.Generator(device=DEV); gen.manual_seed(9)
+L = Lane()
+master = zipf_gaps_gpu(200_000_000, gen)
+for k in (64, 256, 1024):
+    lists = [thin_gpu(master, 0.5 / k, gen) for _ in range(k)]
+    tot = sum(t.numel() for t in lists)
+    out = torch.empty(tot + 8, dtype=torch.int64, device=DEV); out_len = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ms, _ = timeit(lambda: L.merge(lists, out, out_len), warm=2, reps=5)
+    print(json.dumps({"k": k, "total": tot, "ms_tree": round(ms, 3)}), flush=True)
+    del lists, out
 PY
