@@ -595,6 +595,9 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_ops
 
+            # the per-op rows chain producers and consumers on one stream (Decode -> IntersectSorted): measured, like
+            # tools/bench_ops.py alone, on a lane WITHOUT the resident-inputs declaration of the headline loop
+            _lib.check(lib.dgx_lane_set_resident_inputs(lane, 0))
             ops = bench_ops.quick_rows(lib, lane, dev, peak)
         except Exception as e:  # noqa: BLE001
             ops = {"error": repr(e)}

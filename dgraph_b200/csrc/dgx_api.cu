@@ -202,6 +202,26 @@ struct dgx_lane {
     DevArena fws[2];
     cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_pipe[2] = {nullptr, nullptr};
     int fslot = 0;
+    // Buffers the lane's own queued operations write (outputs of filter batches, merges, decodes since the last
+    // dgx_lane_sync).  A batch that reads one of them is NOT planned ahead: its pre-pass is ordered behind the main
+    // stream, so "decode -> intersect" or chained intersections on a resident-inputs lane stay correct.
+    struct OutRange { const char* p; size_t bytes; };
+    std::vector<OutRange> outs;
+    bool outs_overflow = false;
+    cudaEvent_t ev_prod = nullptr;
+    void note_output(const void* p, size_t bytes) {
+        if (!resident_inputs || !p || !bytes) return;
+        for (OutRange& r : outs)
+            if (r.p == (const char*)p) { r.bytes = std::max(r.bytes, bytes); return; }
+        if (outs.size() >= 32) { outs_overflow = true; return; }
+        outs.push_back({(const char*)p, bytes});
+    }
+    bool reads_own_output(const void* p) const {
+        if (outs_overflow) return true;
+        for (const OutRange& r : outs)
+            if ((const char*)p >= r.p && (const char*)p < r.p + r.bytes) return true;
+        return false;
+    }
 };
 // Results up to this many values reach the host in the same round trip as their length.
 constexpr size_t kSpecHead = 8192;
@@ -396,6 +416,7 @@ extern "C" void dgx_lane_destroy(dgx_lane* l) {
         l->fws[i].destroy();
         if (l->ev_plan[i]) cudaEventDestroy(l->ev_plan[i]);
         if (l->ev_pipe[i]) cudaEventDestroy(l->ev_pipe[i]);
+        if (i == 0 && l->ev_prod) cudaEventDestroy(l->ev_prod);
     }
     if (l->own_stream) cudaStreamDestroy(l->stream);
     delete l;
@@ -412,6 +433,7 @@ extern "C" int dgx_lane_set_resident_inputs(dgx_lane* l, int on) {
             CK(cudaEventCreateWithFlags(&l->ev_plan[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&l->ev_pipe[i], cudaEventDisableTiming));
         }
+        CK(cudaEventCreateWithFlags(&l->ev_prod, cudaEventDisableTiming));
     }
     if (!on && l->side) CK(cudaStreamSynchronize(l->side));
     l->resident_inputs = on != 0;
@@ -426,6 +448,8 @@ extern "C" int dgx_lane_sync(dgx_lane* l) {
     CK(cudaStreamSynchronize(l->stream));
     l->host.reset();
     l->ws.release_retired();
+    l->outs.clear();
+    l->outs_overflow = false;
     if (*l->h_err) {
         *l->h_err = 0;
         CK(cudaMemsetAsync(l->d_err, 0, sizeof(int), l->stream));
@@ -537,6 +561,13 @@ static int filter_batch_impl(dgx_lane* l, int op, const ListDesc* lists, const s
         ar = &l->fws[slot];
         pre = l->side;
         CK(cudaStreamWaitEvent(l->side, l->ev_pipe[slot], 0));  // the pipeline that last read this workspace is done
+        bool dep = false;  // a list this lane's own queued work produces: plan it behind that work, not ahead
+        for (size_t i = k_off[0]; i < k_off[nq] && !dep; ++i)
+            dep = l->reads_own_output(lists[i].ptr) || (lists[i].dyn_len && l->reads_own_output(lists[i].dyn_len));
+        if (dep) {
+            CK(cudaEventRecord(l->ev_prod, l->stream));
+            CK(cudaStreamWaitEvent(l->side, l->ev_prod, 0));
+        }
         ar->reset();
     }
     rc = ar->alloc(tasks_b + lists_b + status_b, &d_raw);
@@ -654,7 +685,10 @@ extern "C" int dgx_dev_filter_batch(dgx_lane* l, int op, const uint64_t* const* 
     std::vector<ListDesc> ld(nlists);
     for (size_t i = 0; i < nlists; ++i) ld[i] = {d_lists[i], lens[i], nullptr};
     g_stats.calls += 1;
-    return filter_batch_impl(l, op, ld.data(), k_off, nq, d_out, out_cap, d_out_off);
+    const int rc = filter_batch_impl(l, op, ld.data(), k_off, nq, d_out, out_cap, d_out_off);
+    l->note_output(d_out, out_cap * sizeof(uint64_t));
+    l->note_output(d_out_off, (nq + 1) * sizeof(uint64_t));
+    return rc;
 }
 
 // ---------------------------------------------------------------------------
@@ -945,7 +979,10 @@ extern "C" int dgx_dev_merge_sorted(dgx_lane* l, const uint64_t* const* d_lists,
     std::vector<ListDesc> ld(k);
     for (size_t i = 0; i < k; ++i) ld[i] = {d_lists[i], lens[i], nullptr};
     g_stats.calls += 1;
-    return merge_sorted_impl(l, ld.data(), k, d_out, out_cap, d_out_len);
+    const int rc = merge_sorted_impl(l, ld.data(), k, d_out, out_cap, d_out_len);
+    l->note_output(d_out, out_cap * sizeof(uint64_t));
+    l->note_output(d_out_len, sizeof(uint64_t));
+    return rc;
 }
 
 // ---------------------------------------------------------------------------
@@ -1306,7 +1343,10 @@ extern "C" int dgx_dev_decode(dgx_lane* l, const dgx_dev_pack* pk, uint64_t seek
     if (int rc = lane_begin_op(l)) return rc;
     g_stats.calls += 1;
     g_stats.uids_in += pk->exact_len;
-    return decode_impl(l, pk->pk, seek, d_out, out_cap, d_out_len);
+    const int rc = decode_impl(l, pk->pk, seek, d_out, out_cap, d_out_len);
+    l->note_output(d_out, out_cap * sizeof(uint64_t));
+    l->note_output(d_out_len, sizeof(uint64_t));
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

@@ -297,7 +297,10 @@ void* dgx_lane_stream(dgx_lane* lane);
  * and not written by anything queued on the lane's stream (the contract of a pack / list cache: posting lists are
  * immutable once rolled up).  The plan pre-pass of a batch then runs on a side stream while the pipeline kernel of the
  * previous batch is still busy (its tables alternate between two workspaces).  Results (d_out, d_out_off) stay ordered
- * on the lane's stream as before.  Off by default; the host-pointer entry points never use it. */
+ * on the lane's stream as before.  A batch that reads a buffer this lane's own queued calls write (the output of an
+ * earlier dgx_dev_decode / dgx_dev_merge_sorted / dgx_dev_filter_batch since the last dgx_lane_sync) is recognised by
+ * its address and planned behind them instead of ahead, so chains on one lane stay correct; lists written by OTHER
+ * streams must be complete before the call.  Off by default; the host-pointer entry points never use it. */
 int dgx_lane_set_resident_inputs(dgx_lane* lane, int on);
 /* Number of kernels this lane has launched so far. */
 uint64_t dgx_lane_launches(const dgx_lane* lane);

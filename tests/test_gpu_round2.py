@@ -605,3 +605,60 @@ def test_resident_lane_batches(dgx, orc):
                 eq(ho[int(hoff[qi]): int(hoff[qi + 1])], want, f"resident batch {bi} query {qi} op {op}")
         _lib.check(lib.dgx_lane_set_resident_inputs(lane, 0))
         lib.dgx_lane_destroy(lane)
+
+
+def test_resident_lane_chains(dgx, orc):
+    """A resident-inputs lane whose batches READ what the lane's own queued calls write: Decode -> IntersectSorted and
+    intersection -> intersection chains, no synchronisation in between, the intermediate buffers holding descending
+    garbage beforehand (a plan taken from it would have r0 > r1).  The lane recognises its own outputs by address and
+    plans such a batch behind the producer instead of ahead of it."""
+    import torch
+    from dgraph_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        lane = lib.dgx_lane_create(0, C.c_void_p(stream.cuda_stream))
+        assert lane
+        _lib.check(lib.dgx_lane_set_resident_inputs(lane, 1))
+        rng = np.random.default_rng(81)
+        master = gen.zipf_gaps(rng, 900_000)
+        a = gen.thin(rng, master, 0.8)
+        others = [gen.thin(rng, master, 0.7) for _ in range(4)]
+        pack = to_pack(dgx, orc.encode(a, 256))
+        view = dgx.codec.view_of(pack)
+        pk = C.c_void_p()
+        _lib.check(lib.dgx_dev_pack_upload(lane, C.byref(view), C.byref(pk)))
+        d_oth = [torch.from_numpy(l.view(np.int64).copy()).to(dev) for l in others]
+        garbage = torch.arange(a.size + 8, 0, -1, dtype=torch.int64, device=dev) * 977
+        dec = garbage.clone()
+        dec_len = torch.zeros(1, dtype=torch.int64, device=dev)
+        mid = garbage.clone()                      # result of the first intersection = first list of the second
+        mid_off = torch.zeros(2, dtype=torch.int64, device=dev)
+        fin = torch.empty(a.size + 8, dtype=torch.int64, device=dev)
+        fin_off = torch.zeros(2, dtype=torch.int64, device=dev)
+        want_mid = orc.intersect_sorted([a, others[0], others[1]])
+        want_fin = orc.intersect_sorted([want_mid, others[2], others[3]])
+        torch.cuda.synchronize()
+
+        def batch(lists, lens, out, off):
+            n = len(lists)
+            _lib.check(lib.dgx_dev_filter_batch(lane, 0, (C.c_void_p * n)(*[t.data_ptr() for t in lists]), (C.c_size_t * n)(*lens),
+                                                (C.c_size_t * 2)(0, n), 1, C.c_void_p(out.data_ptr()), a.size, C.c_void_p(off.data_ptr())))
+
+        for rep in range(4):
+            if rep:                                 # garbage again, ordered on the lane's stream
+                dec.copy_(garbage)
+                mid.copy_(garbage)
+            _lib.check(lib.dgx_dev_decode(lane, pk, 0, C.c_void_p(dec.data_ptr()), a.size, C.c_void_p(dec_len.data_ptr())))
+            batch([dec, d_oth[0], d_oth[1]], [a.size, others[0].size, others[1].size], mid, mid_off)
+            # the second batch reads `mid`; its length is known here only because the test knows the answer
+            batch([mid, d_oth[2], d_oth[3]], [want_mid.size, others[2].size, others[3].size], fin, fin_off)
+            torch.cuda.current_stream().synchronize()
+            eq(mid[: int(mid_off[1].item())].cpu().numpy().view(np.uint64), want_mid, f"decode -> intersect, rep {rep}")
+            eq(fin[: int(fin_off[1].item())].cpu().numpy().view(np.uint64), want_fin, f"intersect -> intersect, rep {rep}")
+        _lib.check(lib.dgx_lane_sync(lane))
+        lib.dgx_dev_pack_free(pk)
+        _lib.check(lib.dgx_lane_set_resident_inputs(lane, 0))
+        lib.dgx_lane_destroy(lane)
