@@ -885,7 +885,7 @@ static int merge_multi_impl(dgx_lane* l, const std::vector<MRef>& runs, const st
     const size_t a_tcnt = a_tout + (size_t)(nsamp + 3) * 8;
     const size_t a_tlo = ((a_tcnt + (size_t)(nsamp + 2) * 4 + 255) & ~size_t(255));
     const size_t a_status = a_tlo + (size_t)(nsamp + 2) * 8;
-    const size_t a_end = a_status + (size_t)(nsamp + 3) * 8 + 256;  // look-back words + ticket (merge_radix.cuh)
+    const size_t a_end = a_status + (size_t)(nsamp + 3) * 8 + 256;  // look-back words + ticket (merge_tile32.cuh, DGX_MERGE_LAG)
     rc = l->ws.alloc(a_end, &d_raw);
     if (rc) return rc;
     void* d_scratch;

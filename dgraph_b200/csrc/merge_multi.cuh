@@ -56,7 +56,7 @@ struct MMParams {
     u64 out_cap;
     u64* out_len;
     int* err;
-    // merge_radix.cuh
+    // merge_tile32.cuh
     u32 nbs;                // boundaries per run in the run-major bounds table (bounds[j * nbs + b])
     u64* status;            // look-back words, one per tile, zeroed
     u32* ticket;            // zeroed
